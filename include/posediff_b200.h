@@ -1,0 +1,154 @@
+/*
+ * posediff_b200.h -- C ABI of the B200-native PoseDiffusion sampling hot path.
+ *
+ * The reference (facebookresearch/PoseDiffusion) is pure Python + PyTorch ATen; it has NO C ABI,
+ * plugin or FFI layer.  This header therefore declares the entry points a
+ * reference-side binding (ctypes) needs in order to replace, one for one, the
+ * Python call sites of the hot path:
+ *
+ *   pdb_denoiser_load      <- load_state_dict of `diffuser.model.*`      (pose_diffusion/demo.py:56-57,
+ *                                                                          models/pose_diffusion_model.py:57-61)
+ *   pdb_denoiser_forward   <- Denoiser.forward(x, t, z)                  (models/denoiser.py:53-76)
+ *   pdb_p_sample           <- GaussianDiffusion.p_sample                 (models/gaussian_diffuser.py:249-282)
+ *   pdb_matches_pack       <- matches_dict -> device tensors, pair_idx   (util/geometry_guided_sampling.py:16-45,
+ *                                                                          util/match_extraction.py:50-77 output format)
+ *   pdb_sampson_eval       <- compute_sampson_distance + backward        (util/geometry_guided_sampling.py:129-172)
+ *   pdb_ggs                <- geometry_guided_sampling (5 x GGS_optimize) (util/geometry_guided_sampling.py:14-126)
+ *   pdb_sample_loop        <- GaussianDiffusion.sample / p_sample_loop   (models/gaussian_diffuser.py:285-306)
+ *   pdb_sample_loop_host   <- the same call with HOST buffers (demo.py:108 as a user sees it: features and
+ *                             matches on the host, poses back on the host)
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  `*_dev` pointers are CUDA device pointers
+ * on the context's device, `*_host` are host pointers, `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream).  All floating point data is IEEE fp32 unless stated; pose layout is the
+ * reference's "absT_quaR_logFL" encoding [B, N, 9] = (T xyz, quaternion wxyz, log focal xy), row-major.
+ * Every function returns PDB_OK (0) or a negative pdb_status; pdb_last_error() gives the message.
+ * There is no CPU fallback: every compute entry point fails with PDB_ERR_CUDA if no sm_100 device exists.
+ */
+#ifndef POSEDIFF_B200_H
+#define POSEDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDB_ABI_VERSION 1
+
+typedef enum pdb_status {
+  PDB_OK = 0,
+  PDB_ERR_INVALID = -1,   /* bad argument (mirrors the reference's ValueError / NotImplementedError sites) */
+  PDB_ERR_CUDA = -2,      /* CUDA runtime failure, or no Blackwell device */
+  PDB_ERR_STATE = -3,     /* e.g. weights not loaded */
+  PDB_ERR_LIMIT = -4      /* size beyond a compiled limit (frames > PDB_MAX_FRAMES, ...) */
+} pdb_status;
+
+#define PDB_TARGET_DIM 9       /* models/denoiser.py:26 */
+#define PDB_Z_DIM 384          /* DINO ViT-S/16 CLS width, models/denoiser.py:28 */
+#define PDB_NUM_TIMESTEPS 100  /* models/gaussian_diffuser.py:78 */
+#define PDB_MAX_FRAMES 128     /* frames per sequence supported by the kernels */
+#define PDB_NUM_WEIGHT_TENSORS 108
+#define PDB_GGS_PHASES 5       /* util/geometry_guided_sampling.py:47-64 */
+
+typedef struct pdb_context pdb_context; /* one per (process, GPU) */
+typedef struct pdb_matches pdb_matches; /* device-resident packed correspondences of ONE sequence */
+
+/* cfgs/default.yaml:6-13 -> kwargs of GGS_optimize (util/geometry_guided_sampling.py:74-81). */
+typedef struct pdb_ggs_config {
+  double alpha;         /* 1e-4 */
+  double learning_rate; /* 1e-2 */
+  int32_t iter_num;     /* 100 (doubled for the all-parameter phases, :86-87) */
+  double sampson_max;   /* 10 */
+  double min_matches;   /* 10; <= 0 disables the early exit (:103) */
+  double momentum;      /* 0.9 (hard-coded in the reference, :89) */
+} pdb_ggs_config;
+
+/* What the reference prints per phase ("t=.. | sampson=..", :124) plus the early-exit notice (:107). */
+typedef struct pdb_ggs_stats {
+  float sampson[PDB_GGS_PHASES];    /* mean(min(err, sampson_max)) of the last evaluated iteration */
+  int32_t iters[PDB_GGS_PHASES];    /* SGD updates actually applied in the phase */
+  int32_t dropped[PDB_GGS_PHASES];  /* 1 if the phase stopped on "insufficient valid matches" */
+  int32_t n_valid[PDB_GGS_PHASES];  /* valid matches at the last evaluated iteration */
+} pdb_ggs_stats;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int pdb_abi_version(void);
+int pdb_create(pdb_context** out, int device_ordinal);
+void pdb_destroy(pdb_context* ctx);
+const char* pdb_last_error(const pdb_context* ctx); /* ctx may be NULL: last creation error */
+int pdb_device_info(const pdb_context* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* number of kernels this library has launched since creation (bench.py's gpu_launches) */
+int64_t pdb_launch_count(const pdb_context* ctx);
+
+/* DDPM schedule exactly as GaussianDiffusion.init_diff_hyper builds it (models/gaussian_diffuser.py:136-187;
+ * "custom" = float64 linspace(beta_1, beta_T, 100), cumprod, cast to float32).  HOST-ONLY helper, needs no GPU:
+ * out[100][8] = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
+ * posterior_mean_coef2, exp(0.5*posterior_log_variance_clipped), posterior_log_variance_clipped, betas,
+ * alphas_cumprod}. */
+int pdb_schedule_table(float* out, double beta_1, double beta_T);
+
+/* ---- denoiser weights ---------------------------------------------------------------------------
+ * `tensors[i]` (host or device, fp32, contiguous) in the order of the reference state_dict below
+ * `diffuser.model.`:  time_embed.linear.0.{weight,bias}, time_embed.linear.2.{weight,bias},
+ * _first.{weight[512,702],bias}, then for layer 0..7: self_attn.in_proj_{weight,bias},
+ * self_attn.out_proj.{weight,bias}, linear1.{weight,bias}, linear2.{weight,bias}, norm1.{weight,bias},
+ * norm2.{weight,bias}; then _last.0.{weight,bias}, _last.1.{weight,bias}, _last.3.{weight,bias}.
+ * The library re-lays them out for the kernels and tabulates the timestep-embedding MLP for t in [0,100). */
+int pdb_denoiser_load(pdb_context* ctx, const float* const* tensors, int32_t count, void* stream);
+
+/* eps[B,N,9] = Denoiser(x[B,N,9], t, z[B,N,384]); one integer timestep for the whole batch, as the
+ * sampler uses it (gaussian_diffuser.py:265). */
+int pdb_denoiser_forward(pdb_context* ctx, const float* x_dev, int32_t t, const float* z_dev, int32_t batch,
+                         int32_t frames, float* eps_dev, void* stream);
+
+/* One ancestral step WITHOUT guidance (gaussian_diffuser.py:249-282): writes x0 (may be NULL), the posterior
+ * mean (may be NULL) and pred = mean + sigma_t * noise (noise_dev NULL or t == 0 -> pred = mean). */
+int pdb_p_sample(pdb_context* ctx, const float* x_dev, int32_t t, const float* z_dev, const float* noise_dev,
+                 int32_t batch, int32_t frames, float* pred_dev, float* mean_dev, float* x0_dev, void* stream);
+
+/* ---- correspondences ----------------------------------------------------------------------------
+ * Input is the reference's matches_dict (demo.py:82-87): kp1/kp2 float64 [m,2] pixel coordinates,
+ * i12 int64 [m,2] frame indices, img_shape (frames, 3, height, width).  Rows with equal (i12[0], i12[1])
+ * are expected in contiguous runs (any run order; a pair may recur).  Packed ONCE into device-resident
+ * fp32 (u1,v1,u2,v2) quads, pair-segmented and padded to 32-row rounds; pair/segment indexing is exact.
+ * `on_device` != 0 means the three arrays are device pointers. */
+int pdb_matches_pack(pdb_context* ctx, const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total,
+                     int32_t frames, int32_t height, int32_t width, int32_t on_device, void* stream,
+                     pdb_matches** out);
+void pdb_matches_free(pdb_matches* m);
+int pdb_matches_info(const pdb_matches* m, int64_t* m_total, int32_t* segments, int64_t* rounds, int32_t* frames);
+
+/* compute_sampson_distance + backward for one sequence: grad_dev[N,9] = d mean(valid err) / d pose,
+ * scalars_dev[4] = {loss, n_valid, logged (= mean(min(err, max)) over all matches), 0}.  Optional per-segment
+ * dumps: F_dev[segments,9] (F' = F^T), G_dev[segments,9] (sum over valid matches of d err / d F').
+ * update flags as in GGS_optimize (:71-73). */
+int pdb_sampson_eval(pdb_context* ctx, const pdb_matches* m, const float* pose_dev, int32_t update_R,
+                     int32_t update_T, int32_t update_FL, double sampson_max, float* grad_dev, float* scalars_dev,
+                     float* F_dev, float* G_dev, void* stream);
+
+/* geometry_guided_sampling for `batch` independent sequences: pose_dev[batch, N, 9] is optimised in place.
+ * stats_dev (device, may be NULL) receives `batch` pdb_ggs_stats records, without any host synchronisation. */
+int pdb_ggs(pdb_context* ctx, pdb_matches* const* problems, int32_t batch, float* pose_dev,
+            const pdb_ggs_config* cfg, pdb_ggs_stats* stats_dev, void* stream);
+
+/* ---- sampler ------------------------------------------------------------------------------------
+ * p_sample_loop: draws_dev[T+1, B, N, 9] holds the Gaussian draws in the reference's order (draws[0] = x_T,
+ * draws[1+k] = noise of loop iteration k, i.e. t = T-1-k; unused on guided steps and at t = 0).
+ * problems == NULL -> no guidance.  cond_start_step as in p_sample (:270).  trail_dev may be NULL, else
+ * [T+1, B, N, 9].  stats_dev may be NULL, else [cond_start_step, batch] records (row 0 = first guided step). */
+int pdb_sample_loop(pdb_context* ctx, const float* z_dev, const float* draws_dev, int32_t batch, int32_t frames,
+                    pdb_matches* const* problems, const pdb_ggs_config* cfg, int32_t cond_start_step,
+                    float* pose_dev, float* trail_dev, pdb_ggs_stats* stats_dev, void* stream);
+
+/* The same with host buffers (pinned or pageable): copies z and the draws in, runs, copies pose (and the
+ * optional trajectory / stats) out, synchronises the stream.  This is the end-to-end call bench.py times. */
+int pdb_sample_loop_host(pdb_context* ctx, const float* z_host, const float* draws_host, int32_t batch,
+                         int32_t frames, pdb_matches* const* problems, const pdb_ggs_config* cfg,
+                         int32_t cond_start_step, float* pose_host, float* trail_host, pdb_ggs_stats* stats_host,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEDIFF_B200_H */

@@ -1,0 +1,309 @@
+"""ctypes binding of libposediff_b200.so (include/posediff_b200.h).
+
+PyTorch is used here only for device memory and streams.  There is NO fallback: if the library is
+missing, or no sm_100 GPU is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libposediff_b200.so")
+
+PDB_NUM_WEIGHT_TENSORS = 108
+PDB_GGS_PHASES = 5
+NUM_TIMESTEPS = 100
+TARGET_DIM = 9
+Z_DIM = 384
+MAX_FRAMES = 128
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class GgsConfig(C.Structure):
+    _fields_ = [
+        ("alpha", C.c_double),
+        ("learning_rate", C.c_double),
+        ("iter_num", C.c_int32),
+        ("sampson_max", C.c_double),
+        ("min_matches", C.c_double),
+        ("momentum", C.c_double),
+    ]
+
+
+class GgsStats(C.Structure):
+    _fields_ = [
+        ("sampson", C.c_float * PDB_GGS_PHASES),
+        ("iters", C.c_int32 * PDB_GGS_PHASES),
+        ("dropped", C.c_int32 * PDB_GGS_PHASES),
+        ("n_valid", C.c_int32 * PDB_GGS_PHASES),
+    ]
+
+
+GGS_STATS_DTYPE = np.dtype(
+    [("sampson", np.float32, (PDB_GGS_PHASES,)), ("iters", np.int32, (PDB_GGS_PHASES,)),
+     ("dropped", np.int32, (PDB_GGS_PHASES,)), ("n_valid", np.int32, (PDB_GGS_PHASES,))]
+)
+assert GGS_STATS_DTYPE.itemsize == C.sizeof(GgsStats)
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "pdb_abi_version": (C.c_int, []),
+    "pdb_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "pdb_destroy": (None, [C.c_void_p]),
+    "pdb_last_error": (C.c_char_p, [C.c_void_p]),
+    "pdb_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pdb_launch_count": (C.c_int64, [C.c_void_p]),
+    "pdb_schedule_table": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "pdb_denoiser_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "pdb_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pdb_p_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_matches_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pdb_matches_free": (None, [C.c_void_p]),
+    "pdb_matches_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "pdb_sampson_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_ggs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(GgsConfig), C.c_void_p, C.c_void_p]),
+    "pdb_sample_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_sample_loop_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and bind every symbol the header declares."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeError(
+                    f"{LIB_PATH} is missing: build it with `python -m posediffusion_b200.build` "
+                    "(posediffusion_b200 has no CPU or PyTorch fallback)"
+                )
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in EXPORTS.items():
+                fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def schedule_table(beta_1: float = 1e-4, beta_T: float = 0.1) -> np.ndarray:
+    """[100, 8] float32 DDPM coefficients from the library's host helper (no GPU needed)."""
+    out = np.zeros((NUM_TIMESTEPS, 8), dtype=np.float32)
+    rc = load_library().pdb_schedule_table(out.ctypes.data_as(C.c_void_p), beta_1, beta_T)
+    if rc != 0:
+        raise NativeError(f"pdb_schedule_table failed ({rc})")
+    return out
+
+
+def ggs_config_struct(cfg: Dict) -> GgsConfig:
+    """cfgs/default.yaml GGS section / kwargs of GGS_optimize -> pdb_ggs_config."""
+    enc = cfg.get("pose_encoding_type", "absT_quaR_logFL")
+    if enc != "absT_quaR_logFL":
+        raise ValueError(f"Unknown pose encoding {enc}")  # camera_transform.py:98-99
+    return GgsConfig(
+        alpha=float(cfg.get("alpha", 1e-4)),
+        learning_rate=float(cfg.get("learning_rate", 1e-2)),
+        iter_num=int(cfg.get("iter_num", 100)),
+        sampson_max=float(cfg.get("sampson_max", 10)),
+        min_matches=float(cfg.get("min_matches", 10)),
+        momentum=float(cfg.get("momentum", 0.9)),
+    )
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_dev(t: torch.Tensor, name: str, device: torch.device, shape=None):
+    if not t.is_cuda:
+        raise NativeError(f"{name} must be a CUDA tensor (posediffusion_b200 has no CPU fallback)")
+    if t.device != device:
+        raise NativeError(f"{name} is on {t.device}, context is on {device}")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise NativeError(f"{name} must be contiguous float32")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise NativeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+
+
+class Matches:
+    """Device-resident packed correspondences of one sequence (pdb_matches)."""
+
+    def __init__(self, ctx: "Context", handle: C.c_void_p, frames: int, m_total: int):
+        self.ctx, self.handle, self.frames, self.m_total = ctx, handle, frames, m_total
+        info = (C.c_int64(), C.c_int32(), C.c_int64(), C.c_int32())
+        ctx.lib.pdb_matches_info(handle, *[C.byref(v) for v in info])
+        self.segments, self.rounds = info[1].value, info[2].value
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.pdb_matches_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Context:
+    """One pdb_context per (process, GPU)."""
+
+    _by_device: Dict[int, "Context"] = {}
+
+    def __init__(self, device_index: int):
+        self.lib = load_library()
+        self.device = torch.device("cuda", device_index)
+        handle = C.c_void_p()
+        rc = self.lib.pdb_create(C.byref(handle), device_index)
+        if rc != 0:
+            raise NativeError(f"pdb_create({device_index}) failed: {self.lib.pdb_last_error(None).decode()}")
+        self.handle = handle
+        self.weights_key = None
+
+    @classmethod
+    def get(cls, device) -> "Context":
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device: posediffusion_b200 runs on B200 (sm_100a) only, there is no CPU fallback")
+        device = torch.device(device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        if index not in cls._by_device:
+            cls._by_device[index] = Context(index)
+        return cls._by_device[index]
+
+    def _ok(self, rc: int, what: str):
+        if rc != 0:
+            raise NativeError(f"{what} failed ({rc}): {self.lib.pdb_last_error(self.handle).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pdb_launch_count(self.handle))
+
+    def sm_count(self) -> int:
+        sm, a, b = C.c_int32(), C.c_int32(), C.c_int32()
+        self.lib.pdb_device_info(self.handle, C.byref(sm), C.byref(a), C.byref(b))
+        return sm.value
+
+    # ---- weights --------------------------------------------------------------------------------
+    def load_denoiser(self, tensors: Sequence[torch.Tensor]):
+        if len(tensors) != PDB_NUM_WEIGHT_TENSORS:
+            raise NativeError(f"expected {PDB_NUM_WEIGHT_TENSORS} tensors, got {len(tensors)}")
+        keep = [t.detach().to(dtype=torch.float32).contiguous() for t in tensors]
+        arr = (C.c_void_p * len(keep))(*[C.c_void_p(t.data_ptr()) for t in keep])
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_denoiser_load(self.handle, arr, len(keep), _stream_ptr(self.device)), "pdb_denoiser_load")
+
+    # ---- denoiser / sampler -----------------------------------------------------------------------
+    def denoiser_forward(self, x: torch.Tensor, t: int, z: torch.Tensor) -> torch.Tensor:
+        B, N, _ = x.shape
+        _check_dev(x, "x", self.device, (B, N, TARGET_DIM))
+        _check_dev(z, "z", self.device, (B, N, Z_DIM))
+        eps = torch.empty_like(x)
+        self._ok(self.lib.pdb_denoiser_forward(self.handle, x.data_ptr(), int(t), z.data_ptr(), B, N, eps.data_ptr(),
+                                               _stream_ptr(self.device)), "pdb_denoiser_forward")
+        return eps
+
+    def p_sample(self, x, t: int, z, noise: Optional[torch.Tensor]):
+        B, N, _ = x.shape
+        _check_dev(x, "x", self.device, (B, N, TARGET_DIM))
+        _check_dev(z, "z", self.device, (B, N, Z_DIM))
+        if noise is not None:
+            _check_dev(noise, "noise", self.device, (B, N, TARGET_DIM))
+        pred, mean, x0 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        self._ok(self.lib.pdb_p_sample(self.handle, x.data_ptr(), int(t), z.data_ptr(),
+                                       noise.data_ptr() if noise is not None else None, B, N, pred.data_ptr(),
+                                       mean.data_ptr(), x0.data_ptr(), _stream_ptr(self.device)), "pdb_p_sample")
+        return pred, mean, x0
+
+    # ---- correspondences ------------------------------------------------------------------------
+    def pack_matches(self, matches_dict: Dict) -> Matches:
+        frames, _, height, width = (int(v) for v in matches_dict["img_shape"])
+        kp1 = np.ascontiguousarray(matches_dict["kp1"], dtype=np.float64).reshape(-1, 2)
+        kp2 = np.ascontiguousarray(matches_dict["kp2"], dtype=np.float64).reshape(-1, 2)
+        i12 = np.ascontiguousarray(matches_dict["i12"], dtype=np.int64).reshape(-1, 2)
+        if not (len(kp1) == len(kp2) == len(i12)):
+            raise ValueError("kp1, kp2 and i12 must have the same number of rows")
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.pdb_matches_pack(self.handle, kp1.ctypes.data, kp2.ctypes.data, i12.ctypes.data, len(kp1),
+                                           frames, height, width, 0, _stream_ptr(self.device), C.byref(handle))
+        if rc == -1:
+            raise ValueError(self.lib.pdb_last_error(self.handle).decode())
+        self._ok(rc, "pdb_matches_pack")
+        return Matches(self, handle, frames, len(kp1))
+
+    def sampson_eval(self, matches: Matches, pose: torch.Tensor, update_R=True, update_T=True, update_FL=True,
+                     sampson_max: float = 10.0, dump: bool = False):
+        _check_dev(pose, "pose", self.device, (matches.frames, TARGET_DIM))
+        grad = torch.empty_like(pose)
+        scalars = torch.zeros(4, device=self.device)
+        Fd = torch.zeros(max(matches.segments, 1), 9, device=self.device) if dump else None
+        Gd = torch.zeros(max(matches.segments, 1), 9, device=self.device) if dump else None
+        self._ok(self.lib.pdb_sampson_eval(self.handle, matches.handle, pose.data_ptr(), int(update_R), int(update_T),
+                                           int(update_FL), float(sampson_max), grad.data_ptr(), scalars.data_ptr(),
+                                           Fd.data_ptr() if dump else None, Gd.data_ptr() if dump else None,
+                                           _stream_ptr(self.device)), "pdb_sampson_eval")
+        return grad, scalars, Fd, Gd
+
+    def _problem_array(self, problems: Sequence[Matches]):
+        return (C.c_void_p * len(problems))(*[p.handle for p in problems])
+
+    def ggs(self, problems: Sequence[Matches], pose: torch.Tensor, cfg: Dict, want_stats: bool = True):
+        """In-place geometry-guided sampling on pose [B, N, 9]; returns a device stats tensor (uint8 view) or None."""
+        B = len(problems)
+        _check_dev(pose, "model_mean", self.device, (B, problems[0].frames, TARGET_DIM))
+        stats = torch.zeros(B * GGS_STATS_DTYPE.itemsize, dtype=torch.uint8, device=self.device) if want_stats else None
+        conf = ggs_config_struct(cfg)
+        self._ok(self.lib.pdb_ggs(self.handle, self._problem_array(problems), B, pose.data_ptr(), C.byref(conf),
+                                  stats.data_ptr() if want_stats else None, _stream_ptr(self.device)), "pdb_ggs")
+        return stats
+
+    def sample_loop(self, z: torch.Tensor, draws: torch.Tensor, problems: Optional[Sequence[Matches]], cfg: Optional[Dict],
+                    cond_start_step: int, want_trail: bool = True, want_stats: bool = True):
+        B, N, _ = z.shape
+        _check_dev(z, "z", self.device, (B, N, Z_DIM))
+        _check_dev(draws, "draws", self.device, (NUM_TIMESTEPS + 1, B, N, TARGET_DIM))
+        pose = torch.empty(B, N, TARGET_DIM, device=self.device)
+        trail = torch.empty(NUM_TIMESTEPS + 1, B, N, TARGET_DIM, device=self.device) if want_trail else None
+        guided = max(0, min(int(cond_start_step), NUM_TIMESTEPS)) if problems else 0
+        stats = None
+        if want_stats and guided:
+            stats = torch.zeros(guided * B * GGS_STATS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        conf = ggs_config_struct(cfg) if problems else None
+        self._ok(self.lib.pdb_sample_loop(self.handle, z.data_ptr(), draws.data_ptr(), B, N,
+                                          self._problem_array(problems) if problems else None,
+                                          C.byref(conf) if conf is not None else None, int(cond_start_step), pose.data_ptr(),
+                                          trail.data_ptr() if want_trail else None,
+                                          stats.data_ptr() if stats is not None else None, _stream_ptr(self.device)),
+                 "pdb_sample_loop")
+        return pose, trail, stats
+
+    def sample_loop_host(self, z: np.ndarray, draws: np.ndarray, problems, cfg, cond_start_step: int,
+                         pose_out: np.ndarray, trail_out: Optional[np.ndarray] = None, stats_out: Optional[np.ndarray] = None):
+        """Host-buffer entry (numpy float32 arrays, ideally pinned): the end-to-end call bench.py times."""
+        B, N, _ = z.shape
+        conf = ggs_config_struct(cfg) if problems else None
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_sample_loop_host(self.handle, z.ctypes.data, draws.ctypes.data, B, N,
+                                                   self._problem_array(problems) if problems else None,
+                                                   C.byref(conf) if conf is not None else None, int(cond_start_step),
+                                                   pose_out.ctypes.data, trail_out.ctypes.data if trail_out is not None else None,
+                                                   stats_out.ctypes.data if stats_out is not None else None,
+                                                   _stream_ptr(self.device)), "pdb_sample_loop_host")
+        return pose_out
+
+
+def stats_to_numpy(stats: Optional[torch.Tensor]) -> Optional[np.ndarray]:
+    """Device stats bytes -> structured numpy array (synchronises)."""
+    if stats is None:
+        return None
+    return stats.cpu().numpy().view(GGS_STATS_DTYPE)

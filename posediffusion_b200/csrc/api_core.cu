@@ -1,0 +1,350 @@
+// C-ABI entry points: context, correspondences, Sampson evaluation, geometry-guided sampling.
+// (include/posediff_b200.h documents which reference call site each one replaces.)
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "context.cuh"
+#include "ggs.cuh"
+
+using namespace pdb;
+
+namespace {
+std::string g_create_error;
+
+constexpr int kGgsBatchMax = 16;
+struct GgsBatch {
+  GgsProblem prob[kGgsBatchMax];
+};
+
+template <bool kEval>
+__global__ void __launch_bounds__(kGgsThreads, 1)
+ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P);
+
+size_t ggs_ws_per_problem(int frames) {
+  size_t bytes = 16 + sizeof(float) * 3 * (frames * 7 + kAccTail);  // {bar, cnt[3]} + 3 accumulators
+  return (bytes + 255) / 256 * 256;
+}
+}  // namespace
+
+extern "C" {
+
+int pdb_abi_version(void) { return PDB_ABI_VERSION; }
+
+const char* pdb_last_error(const pdb_context* ctx) {
+  if (!ctx) return g_create_error.c_str();
+  return reinterpret_cast<const Context*>(ctx)->error.c_str();
+}
+
+int pdb_create(pdb_context** out, int device_ordinal) {
+  if (!out) return PDB_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(err) + " (this library has no CPU fallback)";
+    return PDB_ERR_CUDA;
+  }
+  if (device_ordinal < 0 || device_ordinal >= count) {
+    g_create_error = "device ordinal out of range";
+    return PDB_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  if ((err = cudaGetDeviceProperties(&prop, device_ordinal)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(err);
+    return PDB_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "posediff_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return PDB_ERR_CUDA;
+  }
+  if ((err = cudaSetDevice(device_ordinal)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(err);
+    return PDB_ERR_CUDA;
+  }
+  Context* ctx = new (std::nothrow) Context();
+  if (!ctx) return PDB_ERR_CUDA;
+  ctx->device = device_ordinal;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = reinterpret_cast<pdb_context*>(ctx);
+  return PDB_OK;
+}
+
+int pdb_device_info(const pdb_context* c, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  if (!c) return PDB_ERR_INVALID;
+  const Context* ctx = reinterpret_cast<const Context*>(c);
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  return PDB_OK;
+}
+
+int64_t pdb_launch_count(const pdb_context* c) { return c ? reinterpret_cast<const Context*>(c)->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// correspondences
+// ------------------------------------------------------------------------------------------------
+int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total,
+                     int32_t frames, int32_t height, int32_t width, int32_t on_device, void* stream,
+                     pdb_matches** out) {
+  if (!c || !out) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  *out = nullptr;
+  if (m_total < 0 || frames < 1 || height < 1 || width < 1) return ctx->fail(PDB_ERR_INVALID, "bad match set shape");
+  if (frames > PDB_MAX_FRAMES) return ctx->fail(PDB_ERR_LIMIT, "frames %d > PDB_MAX_FRAMES %d", frames, PDB_MAX_FRAMES);
+  if (m_total > 0 && (!kp1 || !kp2 || !i12)) return ctx->fail(PDB_ERR_INVALID, "null match arrays");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  std::vector<double> h1, h2;
+  std::vector<int64_t> hi;
+  if (on_device && m_total > 0) {  // bring reference-format device arrays to the host packer
+    h1.resize(2 * m_total);
+    h2.resize(2 * m_total);
+    hi.resize(2 * m_total);
+    PDB_CUDA(ctx, cudaMemcpyAsync(h1.data(), kp1, sizeof(double) * 2 * m_total, cudaMemcpyDeviceToHost, st));
+    PDB_CUDA(ctx, cudaMemcpyAsync(h2.data(), kp2, sizeof(double) * 2 * m_total, cudaMemcpyDeviceToHost, st));
+    PDB_CUDA(ctx, cudaMemcpyAsync(hi.data(), i12, sizeof(int64_t) * 2 * m_total, cudaMemcpyDeviceToHost, st));
+    PDB_CUDA(ctx, cudaStreamSynchronize(st));
+    kp1 = h1.data();
+    kp2 = h2.data();
+    i12 = hi.data();
+  }
+  // pass 1: maximal runs of equal (a, b) -> segments; pair index a*N+b as the reference (:26) computes it
+  std::vector<int4> segs;
+  long long rounds = 0;
+  for (int64_t i = 0; i < m_total;) {
+    const int64_t a = i12[2 * i], b = i12[2 * i + 1];
+    if (a < 0 || a >= frames || b < 0 || b >= frames)
+      return ctx->fail(PDB_ERR_INVALID, "i12[%lld] = (%lld, %lld) outside [0, %d)", (long long)i, (long long)a, (long long)b, frames);
+    int64_t j = i + 1;
+    while (j < m_total && i12[2 * j] == a && i12[2 * j + 1] == b) ++j;
+    int64_t remaining = j - i, start = i;
+    while (remaining > 0) {  // keep per-segment counts inside int32
+      const int64_t take = remaining > (1 << 30) ? (1 << 30) : remaining;
+      segs.push_back(make_int4((int)rounds, (int)take, (int)a, (int)b));
+      rounds += (take + 31) / 32;
+      remaining -= take;
+      start += take;
+    }
+    i = j;
+  }
+  if (rounds > 0x7fffffffLL / 32) return ctx->fail(PDB_ERR_LIMIT, "too many matches");
+  const int nseg = (int)segs.size();
+  segs.push_back(make_int4((int)rounds, 0, 0, 0));
+  // pass 2: fp32 quads, padded to 32-row rounds per segment
+  std::vector<float4> pts((size_t)rounds * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+  {
+    int64_t src = 0;
+    for (int s = 0; s < nseg; ++s) {
+      float4* dst = pts.data() + (size_t)segs[s].x * 32;
+      for (int k = 0; k < segs[s].y; ++k, ++src)
+        dst[k] = make_float4((float)kp1[2 * src], (float)kp1[2 * src + 1], (float)kp2[2 * src], (float)kp2[2 * src + 1]);
+    }
+  }
+  Matches* m = new (std::nothrow) Matches();
+  if (!m) return ctx->fail(PDB_ERR_CUDA, "out of host memory");
+  m->ctx = ctx;
+  m->nseg = nseg;
+  m->rounds = (int)rounds;
+  m->m_total = m_total;
+  m->frames = frames;
+  m->height = height;
+  m->width = width;
+  cudaError_t err = cudaMalloc(&m->pts, sizeof(float4) * (pts.size() ? pts.size() : 1));
+  if (err == cudaSuccess) err = cudaMalloc(&m->segs, sizeof(int4) * segs.size());
+  if (err == cudaSuccess && !pts.empty()) err = cudaMemcpyAsync(m->pts, pts.data(), sizeof(float4) * pts.size(), cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(m->segs, segs.data(), sizeof(int4) * segs.size(), cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);  // the host vectors die at return
+  if (err != cudaSuccess) {
+    pdb_matches_free(reinterpret_cast<pdb_matches*>(m));
+    return ctx->fail(PDB_ERR_CUDA, "match upload failed: %s", cudaGetErrorString(err));
+  }
+  *out = reinterpret_cast<pdb_matches*>(m);
+  return PDB_OK;
+}
+
+void pdb_matches_free(pdb_matches* pm) {
+  if (!pm) return;
+  Matches* m = reinterpret_cast<Matches*>(pm);
+  if (m->pts) cudaFree(m->pts);
+  if (m->segs) cudaFree(m->segs);
+  delete m;
+}
+
+int pdb_matches_info(const pdb_matches* pm, int64_t* m_total, int32_t* segments, int64_t* rounds, int32_t* frames) {
+  if (!pm) return PDB_ERR_INVALID;
+  const Matches* m = reinterpret_cast<const Matches*>(pm);
+  if (m_total) *m_total = m->m_total;
+  if (segments) *segments = m->nseg;
+  if (rounds) *rounds = m->rounds;
+  if (frames) *frames = m->frames;
+  return PDB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// GGS launch plumbing (shared with the sampler in api_sampler.cu)
+// ------------------------------------------------------------------------------------------------
+namespace {
+template <bool kEval>
+__global__ void __launch_bounds__(kGgsThreads, 1)
+ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P) {
+  ggs_body<kEval>(batch.prob[blockIdx.x / P.ctas_per_problem], P);
+}
+
+template <bool kEval>
+int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_frames, long long max_rounds,
+                     GgsParams P, cudaStream_t st) {
+  int cpp = ctx->sm_count / nprob;
+  if (cpp < 1) cpp = 1;
+  long long want = max_rounds / 32;  // at least ~1 round per warp
+  if (want < 1) want = 1;
+  if (cpp > want) cpp = (int)want;
+  P.ctas_per_problem = cpp;
+  const size_t smem = ggs_smem_bytes(max_frames);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[kEval]) {
+    PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    attr_set[kEval] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cpp * nprob);
+  cfg.blockDim = dim3(kGgsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ggs_entry<kEval>, batch, P));
+  ctx->launches += 1;
+  return PDB_OK;
+}
+}  // namespace
+
+namespace pdb {
+
+// Enqueue geometry-guided sampling for `batch` sequences (pose_dev [batch, N, 9] updated in place).
+int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* pose_dev, const pdb_ggs_config* cfg,
+                pdb_ggs_stats* stats_dev, cudaStream_t st) {
+  if (batch < 1 || !problems || !pose_dev || !cfg) return ctx->fail(PDB_ERR_INVALID, "bad GGS arguments");
+  if (cfg->iter_num < 0) return ctx->fail(PDB_ERR_INVALID, "iter_num < 0");
+  int max_frames = 0;
+  size_t ws_need = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (!problems[b]) return ctx->fail(PDB_ERR_INVALID, "null match set %d", b);
+    const Matches* m = reinterpret_cast<const Matches*>(problems[b]);
+    if (m->frames != reinterpret_cast<const Matches*>(problems[0])->frames)
+      return ctx->fail(PDB_ERR_INVALID, "all sequences of a batch must have the same frame count");
+    max_frames = max_frames > m->frames ? max_frames : m->frames;
+    ws_need += ggs_ws_per_problem(m->frames);
+  }
+  if (int rc = ensure_buffer(ctx, &ctx->ggs_ws, &ctx->ggs_ws_bytes, ws_need)) return rc;
+  PDB_CUDA(ctx, cudaMemsetAsync(ctx->ggs_ws, 0, ws_need, st));
+  GgsParams P = {};
+  P.n_phases = PDB_GGS_PHASES;
+  const int n = cfg->iter_num;
+  const int iters[PDB_GGS_PHASES] = {2 * n, n, n, n, 2 * n};           // :86-87
+  const int flags[PDB_GGS_PHASES] = {7, 4, 1, 2, 7};                     // all | FL | R | T | all (:47-64)
+  for (int i = 0; i < PDB_GGS_PHASES; ++i) {
+    P.iters[i] = iters[i];
+    P.flags[i] = flags[i];
+  }
+  P.alpha = (float)cfg->alpha;
+  P.lr = (float)cfg->learning_rate;
+  P.smax = (float)cfg->sampson_max;
+  P.momentum = (float)cfg->momentum;
+  P.min_matches = cfg->min_matches;
+  const int N = max_frames;
+  char* ws = static_cast<char*>(ctx->ggs_ws);
+  for (int b0 = 0; b0 < batch; b0 += kGgsBatchMax) {
+    const int nb = (batch - b0) < kGgsBatchMax ? (batch - b0) : kGgsBatchMax;
+    GgsBatch gb = {};
+    long long max_rounds = 1;
+    for (int i = 0; i < nb; ++i) {
+      const Matches* m = reinterpret_cast<const Matches*>(problems[b0 + i]);
+      GgsProblem& p = gb.prob[i];
+      p.pts = m->pts;
+      p.segs = m->segs;
+      p.nseg = m->nseg;
+      p.rounds = m->rounds;
+      p.m_total = m->m_total;
+      p.frames = m->frames;
+      p.height = (float)m->height;
+      p.width = (float)m->width;
+      p.pose = pose_dev + (size_t)(b0 + i) * N * 9;
+      p.bar = reinterpret_cast<unsigned*>(ws);
+      p.gcnt = reinterpret_cast<int*>(ws + 4);
+      p.gacc = reinterpret_cast<float*>(ws + 16);
+      p.stats = stats_dev ? stats_dev + (b0 + i) : nullptr;
+      ws += ggs_ws_per_problem(m->frames);
+      max_rounds = max_rounds > m->rounds ? max_rounds : m->rounds;
+    }
+    if (int rc = launch_ggs_chunk<false>(ctx, gb, nb, max_frames, max_rounds, P, st)) return rc;
+  }
+  return PDB_OK;
+}
+
+}  // namespace pdb
+
+extern "C" {
+
+int pdb_ggs(pdb_context* c, pdb_matches* const* problems, int32_t batch, float* pose_dev, const pdb_ggs_config* cfg,
+            pdb_ggs_stats* stats_dev, void* stream) {
+  if (!c) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return enqueue_ggs(ctx, problems, batch, pose_dev, cfg, stats_dev, static_cast<cudaStream_t>(stream));
+}
+
+int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_dev, int32_t update_R, int32_t update_T,
+                     int32_t update_FL, double sampson_max, float* grad_dev, float* scalars_dev, float* F_dev,
+                     float* G_dev, void* stream) {
+  if (!c) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  if (!pm || !pose_dev || !grad_dev || !scalars_dev) return ctx->fail(PDB_ERR_INVALID, "null argument");
+  const Matches* m = reinterpret_cast<const Matches*>(pm);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t ws_need = ggs_ws_per_problem(m->frames);
+  if (int rc = ensure_buffer(ctx, &ctx->ggs_ws, &ctx->ggs_ws_bytes, ws_need)) return rc;
+  PDB_CUDA(ctx, cudaMemsetAsync(ctx->ggs_ws, 0, ws_need, st));
+  if (G_dev) PDB_CUDA(ctx, cudaMemsetAsync(G_dev, 0, sizeof(float) * 9 * (m->nseg ? m->nseg : 1), st));
+  GgsParams P = {};
+  P.n_phases = 1;
+  P.iters[0] = 1;
+  P.flags[0] = (update_R ? 1 : 0) | (update_T ? 2 : 0) | (update_FL ? 4 : 0);
+  P.alpha = 1e-4f;
+  P.lr = 1e-2f;
+  P.smax = (float)sampson_max;
+  P.momentum = 0.9f;
+  P.min_matches = 0.0;
+  GgsBatch gb = {};
+  GgsProblem& p = gb.prob[0];
+  char* ws = static_cast<char*>(ctx->ggs_ws);
+  p.pts = m->pts;
+  p.segs = m->segs;
+  p.nseg = m->nseg;
+  p.rounds = m->rounds;
+  p.m_total = m->m_total;
+  p.frames = m->frames;
+  p.height = (float)m->height;
+  p.width = (float)m->width;
+  p.pose = const_cast<float*>(pose_dev);  // eval mode never writes the pose
+  p.bar = reinterpret_cast<unsigned*>(ws);
+  p.gcnt = reinterpret_cast<int*>(ws + 4);
+  p.gacc = reinterpret_cast<float*>(ws + 16);
+  p.dbg_grad = grad_dev;
+  p.dbg_scalars = scalars_dev;
+  p.dbg_F = F_dev;
+  p.dbg_G = G_dev;
+  return launch_ggs_chunk<true>(ctx, gb, 1, m->frames, m->rounds > 0 ? m->rounds : 1, P, st);
+}
+
+}  // extern "C"

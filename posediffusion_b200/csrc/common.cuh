@@ -1,0 +1,98 @@
+// Shared device/host helpers for the posediff_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pdb {
+
+constexpr int kTargetDim = 9;
+constexpr int kMaxFrames = 128;
+
+// ---------------------------------------------------------------------------------------------
+// Warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Reduce 16 per-lane values across the 32 lanes of a warp with 16 shuffles (instead of 80):
+// at every butterfly step each lane hands half of its slots to its partner.  On return lane L
+// (both lanes of a pair L, L^1 hold the same value) owns slot  ((L>>4)&1)*8 + ((L>>3)&1)*4 +
+// ((L>>2)&1)*2 + ((L>>1)&1)  in v[0].  Summation order is fixed -> deterministic.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float send = hi ? v[i] : v[i + 8];
+      float keep = hi ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float send = hi ? v[i] : v[i + 4];
+      float keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = hi ? v[i] : v[i + 2];
+      float keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool hi = lane & 2;
+    float send = hi ? v[0] : v[1];
+    float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+__device__ __forceinline__ int warp_reduce16_slot(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Memory helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier for a group of co-resident CTAs (cooperative launch).  `counter` only ever grows;
+// the caller passes the arrival count that marks this barrier as complete.
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    red_release_add_u32(counter, 1u);
+    while (ld_acquire_u32(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+}  // namespace pdb

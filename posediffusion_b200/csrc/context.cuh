@@ -1,0 +1,74 @@
+// Host-side state behind the opaque C handles.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "posediff_b200.h"
+
+namespace pdb {
+
+struct DenoiserWeights;  // denoiser.cuh
+
+struct Context {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t smem_optin = 0;
+  std::string error;
+  long long launches = 0;
+  // GGS workspace (grown on demand)
+  void* ggs_ws = nullptr;
+  size_t ggs_ws_bytes = 0;
+  // denoiser
+  DenoiserWeights* weights = nullptr;
+  void* den_ws = nullptr;
+  size_t den_ws_bytes = 0;
+  // staging for the host-buffer entry point
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    error = buf;
+    return code;
+  }
+};
+
+struct Matches {
+  Context* ctx = nullptr;
+  float4* pts = nullptr;   // [rounds*32]
+  int4* segs = nullptr;    // [nseg+1]
+  int nseg = 0;
+  int rounds = 0;
+  long long m_total = 0;
+  int frames = 0;
+  int height = 0, width = 0;
+};
+
+#define PDB_CUDA(ctx, call)                                                                          \
+  do {                                                                                               \
+    cudaError_t err__ = (call);                                                                      \
+    if (err__ != cudaSuccess)                                                                        \
+      return (ctx)->fail(PDB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+inline int ensure_buffer(Context* ctx, void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return PDB_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  size_t grow = need + need / 4 + 4096;
+  PDB_CUDA(ctx, cudaMalloc(ptr, grow));
+  *have = grow;
+  return PDB_OK;
+}
+
+}  // namespace pdb

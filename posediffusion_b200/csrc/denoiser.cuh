@@ -1,0 +1,445 @@
+// Denoiser forward + DDPM posterior update as ONE persistent cooperative kernel per launch
+// (models/denoiser.py:53-76, util/embedding.py:13-50, models/gaussian_diffuser.py:190-282).
+//
+// A launch runs diffusion steps t_hi .. t_lo back to back.  Per step the grid walks 43 stages separated by
+// group barriers: embed+first, 8 x (LN1+QKV, attention, out-proj+residual, LN2+FF1+ReLU, FF2+residual),
+// last0, tail (LayerNorm(128)+ReLU+Linear(128->9) fused with x0 / posterior mean / noise add).
+// Loop-invariant work is hoisted: z-projection (385 of the 702 `_first` input columns) once per launch,
+// the timestep-embedding MLP and its `_first` block once per weight load (table of 100 rows).
+//
+// This file is the exact-fp32 engine: CUDA-core FMAs, weights re-laid out k4-major ([K/4][O] float4) so that a
+// warp reads 512 contiguous bytes per step while every lane owns one output feature; activations of a token tile
+// are staged in shared memory and broadcast.  S = B*N tokens is tiny (20..160 per GPU): every stage is
+// latency / weight-bandwidth bound.
+#pragma once
+#include "common.cuh"
+#include "posediff_b200.h"
+
+namespace pdb {
+
+constexpr int kDM = 512;       // d_model            (cfgs/default.yaml:28)
+constexpr int kHeads = 4;      // nhead              (:29)
+constexpr int kHD = 128;       // head dim
+constexpr int kFF = 1024;      // dim_feedforward    (:30)
+constexpr int kLayers = 8;     // num_encoder_layers (:31)
+constexpr int kHid = 128;      // mlp_hidden_dim     (denoiser.py:29)
+constexpr int kZ = 384;
+constexpr int kTEmb = 128;
+constexpr int kPoseEmb = 189;  // 9 * (2*10 + 1)
+constexpr int kPoseEmbPad = 192;
+constexpr int kFirstIn = 702;
+constexpr int kT = PDB_NUM_TIMESTEPS;
+constexpr int kDenThreads = 256;
+constexpr int kDenWarps = kDenThreads / 32;
+constexpr float kLnEps = 1e-5f;
+
+struct LayerWeights {
+  const float4* w_qkv;  // packed [512/4][1536]
+  const float* b_qkv;
+  const float4* w_out;  // [512/4][512]
+  const float* b_out;
+  const float4* w_ff1;  // [512/4][1024]
+  const float* b_ff1;
+  const float4* w_ff2;  // [1024/4][512]
+  const float* b_ff2;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct DenoiserDev {  // device pointers into the packed weight arena
+  const float4* w_first_x;  // [192/4][512]  (harmonic-pose columns 0..188 of _first.weight, zero padded)
+  const float4* w_first_z;  // [384/4][512]  (columns 317..700)
+  const float* w_first_pivot;  // [512]      (column 701)
+  const float* b_first;        // [512]
+  const float* tproj;          // [100][512]  = t_emb(t) @ _first.weight[:,189:317]^T
+  LayerWeights layer[kLayers];
+  const float4* w_last0;  // [512/4][128]
+  const float* b_last0;
+  const float *ln_last_g, *ln_last_b;
+  const float* w_last3;  // [9][128] row-major (as in the checkpoint)
+  const float* b_last3;
+  const float* sched;    // [100][8]: a_t, b_t, c1_t, c2_t, sigma_t
+};
+
+struct DenoiserRun {
+  int batch, frames, tokens;
+  int t_hi, t_lo;          // steps t_hi, t_hi-1, ..., t_lo
+  int guide_below;         // t < guide_below: leave the posterior mean in x (no noise; the GGS kernel follows)
+  int compute_zproj;       // 1: (re)compute the z projection at the start of this launch
+  float* x;                // [S,9] sampler state, updated in place
+  const float* z;          // [S,384]
+  const float* draws;      // [T+1,S,9] or null (no noise added)
+  float* trail;            // [T+1,S,9] or null
+  float* eps_out;          // [S,9] or null (network output of the LAST step run)
+  float* x0_out;           // [S,9] or null
+  float* mean_out;         // [S,9] or null
+  // workspace
+  float *zproj, *h, *qkv, *att, *ff, *u;
+  unsigned* bar;           // zero on entry
+};
+
+inline size_t denoiser_ws_floats(int tokens) {
+  return (size_t)tokens * (kDM + kDM + 3 * kDM + kDM + kFF + kHid) + 64;
+}
+
+// ---------------------------------------------------------------------------------------------
+// token-tile loaders (global -> shared), one warp per row
+// ---------------------------------------------------------------------------------------------
+// plain copy or LayerNorm of a [rows, K] slab; rows >= valid are zero-filled
+template <int K>
+__device__ __forceinline__ void load_rows(float* __restrict__ Xs, const float* __restrict__ src, int row0, int rows,
+                                          int valid_end, const float* __restrict__ ln_g, const float* __restrict__ ln_b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int PER = K / 128;  // float4 per lane
+  for (int r = warp; r < rows; r += kDenWarps) {
+    const int s = row0 + r;
+    float4 v[PER];
+    if (s < valid_end) {
+      const float4* p = reinterpret_cast<const float4*>(src + (size_t)s * K);
+#pragma unroll
+      for (int i = 0; i < PER; ++i) v[i] = __ldcg(p + lane + 32 * i);
+      if (ln_g) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        const float mean = warp_sum(sum) * (1.0f / K);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+          sq += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / K) + kLnEps);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g) + lane + 32 * i);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ln_b) + lane + 32 * i);
+          v[i].x = v[i].x * rstd * g.x + b.x;
+          v[i].y = v[i].y * rstd * g.y + b.y;
+          v[i].z = v[i].z * rstd * g.z + b.z;
+          v[i].w = v[i].w * rstd * g.w + b.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4* d = reinterpret_cast<float4*>(Xs + (size_t)r * K);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) d[lane + 32 * i] = v[i];
+  }
+}
+
+// harmonic pose embedding (pytorch3d HarmonicEmbedding, n=10, logspace, append_input; embedding.py:44):
+// [sin(x_c 2^k) (c-major) | cos(same) | x | 0 0 0]
+__device__ __forceinline__ void load_pose_embed(float* __restrict__ Xs, const float* __restrict__ x, int row0, int rows,
+                                                int valid_end) {
+  for (int i = threadIdx.x; i < rows * kPoseEmbPad; i += kDenThreads) {
+    const int r = i / kPoseEmbPad, col = i - r * kPoseEmbPad;
+    const int s = row0 + r;
+    float v = 0.f;
+    if (s < valid_end && col < kPoseEmb) {
+      if (col < 180) {
+        const int j = col < 90 ? col : col - 90;
+        const int c = j / 10, k = j - c * 10;
+        const float arg = __ldcg(x + s * 9 + c) * (float)(1 << k);
+        v = col < 90 ? sinf(arg) : cosf(arg);
+      } else {
+        v = __ldcg(x + s * 9 + (col - 180));
+      }
+    }
+    Xs[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One linear work item: 32 output features x one token tile.  Xs = staged activations [TS][K].
+// ---------------------------------------------------------------------------------------------
+enum : int { kEpiNone = 0, kEpiRelu = 1, kEpiSilu = 2 };
+
+template <int TS, int K>
+__device__ __forceinline__ void linear_item(const float* __restrict__ Xs, float* __restrict__ red,
+                                            const float4* __restrict__ Wp, int O, int o0, const float* __restrict__ bias,
+                                            const float* __restrict__ add1, int ld1, const float* __restrict__ add2,
+                                            const float* __restrict__ add_row_scaled, const float* __restrict__ row_scale,
+                                            float* __restrict__ Y, int ldy, int row0, int valid_end, int epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int K4 = K / 4;
+  constexpr int PERW = K4 / kDenWarps;           // k4 rows per warp
+  constexpr int BATCH = PERW < 16 ? PERW : 16;   // weight loads in flight
+  static_assert(K4 % kDenWarps == 0 && PERW % BATCH == 0, "K layout");
+  float acc[TS];
+#pragma unroll
+  for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+  const float4* wp = Wp + (size_t)(warp * PERW) * O + o0 + lane;
+  const float* xs = Xs + warp * PERW * 4;
+#pragma unroll 1
+  for (int b = 0; b < PERW; b += BATCH) {
+    float4 w[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) w[i] = __ldg(wp + (size_t)(b + i) * O);
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + s * K + (b + i) * 4);
+        acc[s] = fmaf(w[i].x, xv.x, fmaf(w[i].y, xv.y, fmaf(w[i].z, xv.z, fmaf(w[i].w, xv.w, acc[s]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < TS; ++s) red[(warp * TS + s) * 32 + lane] = acc[s];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TS * 32; idx += kDenThreads) {
+    const int s = idx >> 5, f = idx & 31;
+    const int row = row0 + s, o = o0 + f;
+    if (row < valid_end) {
+      float v = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kDenWarps; ++wv) v += red[(wv * TS + s) * 32 + f];
+      if (bias) v += __ldg(bias + o);
+      if (add1) v += __ldcg(add1 + (size_t)row * ld1 + o);
+      if (add2) v += __ldg(add2 + o);
+      if (add_row_scaled) v += __ldg(add_row_scaled + o) * row_scale[s];
+      if (epi == kEpiRelu) v = fmaxf(v, 0.f);
+      else if (epi == kEpiSilu) v = v / (1.0f + expf(-v));
+      Y[(size_t)row * ldy + o] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self-attention for one (sequence, head): N <= 128 keys, head dim 128, fp32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void attention_item(float* __restrict__ smem, const float* __restrict__ qkv,
+                                               float* __restrict__ att, int seq, int head, int N) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int KP = kHD + 1;  // padded key rows: lane = key index reads are conflict free
+  float* Ks = smem;                 // [N][129]
+  float* Vs = Ks + N * KP;          // [N][128]
+  float* Qs = Vs + N * kHD;         // [warps][128]
+  float* Ps = Qs + kDenWarps * kHD; // [warps][128]
+  const float* base = qkv + (size_t)seq * N * (3 * kDM) + head * kHD;
+  for (int i = threadIdx.x; i < N * (kHD / 4); i += kDenThreads) {
+    const int j = i / (kHD / 4), d4 = i - j * (kHD / 4);
+    const float4 kv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + kDM) + d4);
+    const float4 vv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + 2 * kDM) + d4);
+    Ks[j * KP + d4 * 4 + 0] = kv.x; Ks[j * KP + d4 * 4 + 1] = kv.y; Ks[j * KP + d4 * 4 + 2] = kv.z; Ks[j * KP + d4 * 4 + 3] = kv.w;
+    *reinterpret_cast<float4*>(Vs + j * kHD + d4 * 4) = vv;
+  }
+  __syncthreads();
+  const float scaling = 0.08838834764831845f;  // 1/sqrt(128): q is scaled before QK^T (torch MHA)
+  for (int i = warp; i < N; i += kDenWarps) {
+    const float4 qv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)i * 3 * kDM) + lane);
+    *reinterpret_cast<float4*>(Qs + warp * kHD + lane * 4) = make_float4(qv.x * scaling, qv.y * scaling, qv.z * scaling, qv.w * scaling);
+    __syncwarp();
+    float sc[4];  // up to 128 keys: 4 passes of 32
+    float mx = -INFINITY;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int j = p * 32 + lane;
+      float dot = -INFINITY;
+      if (p * 32 < N) {
+        if (j < N) {
+          dot = 0.f;
+          const float* kr = Ks + j * KP;
+          const float* qr = Qs + warp * kHD;
+#pragma unroll 16
+          for (int d = 0; d < kHD; ++d) dot = fmaf(qr[d], kr[d], dot);
+        }
+      }
+      sc[p] = dot;
+      mx = fmaxf(mx, dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int j = p * 32 + lane;
+      const float e = (j < N) ? expf(sc[p] - mx) : 0.f;
+      sc[p] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int j = p * 32 + lane;
+      if (j < N) Ps[warp * kHD + j] = sc[p] * inv;
+    }
+    __syncwarp();
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < N; ++j) {
+      const float pj = Ps[warp * kHD + j];
+      const float4 vv = *reinterpret_cast<const float4*>(Vs + j * kHD + lane * 4);
+      o4.x = fmaf(pj, vv.x, o4.x); o4.y = fmaf(pj, vv.y, o4.y); o4.z = fmaf(pj, vv.z, o4.z); o4.w = fmaf(pj, vv.w, o4.w);
+    }
+    *reinterpret_cast<float4*>(att + ((size_t)seq * N + i) * kDM + head * kHD + lane * 4) = o4;
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tail: per token LayerNorm(128) + ReLU + Linear(128->9), then the DDPM arithmetic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tail_token(const DenoiserDev& W, const DenoiserRun& R, int s, int t, bool last_step) {
+  const int lane = threadIdx.x & 31;
+  float4 v = __ldcg(reinterpret_cast<const float4*>(R.u + (size_t)s * kHid) + lane);
+  const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / kHid);
+  v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+  const float rstd = 1.0f / sqrtf(warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) * (1.0f / kHid) + kLnEps);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(W.ln_last_g) + lane);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(W.ln_last_b) + lane);
+  v.x = fmaxf(v.x * rstd * g.x + b.x, 0.f);
+  v.y = fmaxf(v.y * rstd * g.y + b.y, 0.f);
+  v.z = fmaxf(v.z * rstd * g.z + b.z, 0.f);
+  v.w = fmaxf(v.w * rstd * g.w + b.w, 0.f);
+  float mine = 0.f;
+#pragma unroll
+  for (int c = 0; c < kTargetDim; ++c) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W.w_last3 + c * kHid) + lane);
+    const float dot = warp_sum(w.x * v.x + w.y * v.y + w.z * v.z + w.w * v.w);
+    if (lane == c) mine = dot + __ldg(W.b_last3 + c);
+  }
+  if (lane < kTargetDim) {
+    const float* sc = W.sched + t * 8;
+    const size_t e = (size_t)s * kTargetDim + lane;
+    const float xt = R.x[e];
+    const float x0 = sc[0] * xt - sc[1] * mine;             // predict_start_from_noise (:190-194)
+    const float mu = sc[2] * x0 + sc[3] * xt;               // q_posterior mean (:201-205)
+    float out = mu;
+    const int k = (kT - 1) - t;                              // loop iteration index -> draw slot 1 + k
+    if (t >= R.guide_below && t > 0 && R.draws) out = mu + sc[4] * __ldg(R.draws + (size_t)(1 + k) * R.tokens * kTargetDim + e);
+    R.x[e] = out;
+    if (R.trail && t >= R.guide_below) R.trail[(size_t)(1 + k) * R.tokens * kTargetDim + e] = out;
+    if (last_step) {
+      if (R.eps_out) R.eps_out[e] = mine;
+      if (R.x0_out) R.x0_out[e] = x0;
+      if (R.mean_out) R.mean_out[e] = mu;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The persistent kernel
+// ---------------------------------------------------------------------------------------------
+template <int TS>
+__global__ void __launch_bounds__(kDenThreads, 1)
+denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R) {
+  extern __shared__ __align__(16) float smem[];
+  float* Xs = smem;  // [TS][K<=1024] or attention scratch
+  const int S = R.tokens;
+  const int tiles = (S + TS - 1) / TS;
+  const int G = gridDim.x;
+  unsigned bar_count = 0;
+  auto barrier = [&]() {
+    ++bar_count;
+    group_barrier(R.bar, bar_count * (unsigned)G);
+  };
+  // ---- loop-invariant: zproj = z @ Wz^T + b_first + pivot * w_pivot   (denoiser.py:62-70) ----
+  if (R.compute_zproj) {
+    float* red = Xs + TS * kZ;
+    for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
+      const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
+      load_rows<kZ>(Xs, R.z, tt * TS, TS, S, nullptr, nullptr);
+      __shared__ float pivot[32];
+      if (threadIdx.x < TS) pivot[threadIdx.x] = ((tt * TS + threadIdx.x) % R.frames == 0) ? 1.f : 0.f;
+      __syncthreads();
+      linear_item<TS, kZ>(Xs, red, W.w_first_z, kDM, fg * 32, W.b_first, nullptr, 0, nullptr, W.w_first_pivot, pivot,
+                          R.zproj, kDM, tt * TS, S, kEpiNone);
+    }
+    barrier();
+  }
+  for (int t = R.t_hi; t >= R.t_lo; --t) {
+    // ---- embed + first ----
+    {
+      float* red = Xs + TS * kPoseEmbPad;
+      for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
+        const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
+        load_pose_embed(Xs, R.x, tt * TS, TS, S);
+        __syncthreads();
+        linear_item<TS, kPoseEmbPad>(Xs, red, W.w_first_x, kDM, fg * 32, nullptr, R.zproj, kDM, W.tproj + t * kDM, nullptr,
+                                     nullptr, R.h, kDM, tt * TS, S, kEpiNone);
+      }
+      barrier();
+    }
+    for (int l = 0; l < kLayers; ++l) {
+      const LayerWeights& L = W.layer[l];
+      {  // LN1 + QKV projection
+        float* red = Xs + TS * kDM;
+        for (int item = blockIdx.x; item < tiles * (3 * kDM / 32); item += G) {
+          const int tt = item / (3 * kDM / 32), fg = item - tt * (3 * kDM / 32);
+          load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln1_g, L.ln1_b);
+          __syncthreads();
+          linear_item<TS, kDM>(Xs, red, L.w_qkv, 3 * kDM, fg * 32, L.b_qkv, nullptr, 0, nullptr, nullptr, nullptr, R.qkv,
+                               3 * kDM, tt * TS, S, kEpiNone);
+        }
+        barrier();
+      }
+      {  // attention per (sequence, head)
+        for (int item = blockIdx.x; item < R.batch * kHeads; item += G)
+          attention_item(Xs, R.qkv, R.att, item / kHeads, item % kHeads, R.frames);
+        barrier();
+      }
+      {  // out-proj + residual (in place on h: each element is read and written by the same thread)
+        float* red = Xs + TS * kDM;
+        for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
+          const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
+          load_rows<kDM>(Xs, R.att, tt * TS, TS, S, nullptr, nullptr);
+          __syncthreads();
+          linear_item<TS, kDM>(Xs, red, L.w_out, kDM, fg * 32, L.b_out, R.h, kDM, nullptr, nullptr, nullptr, R.h, kDM,
+                               tt * TS, S, kEpiNone);
+        }
+        barrier();
+      }
+      {  // LN2 + FF1 + ReLU
+        float* red = Xs + TS * kDM;
+        for (int item = blockIdx.x; item < tiles * (kFF / 32); item += G) {
+          const int tt = item / (kFF / 32), fg = item - tt * (kFF / 32);
+          load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln2_g, L.ln2_b);
+          __syncthreads();
+          linear_item<TS, kDM>(Xs, red, L.w_ff1, kFF, fg * 32, L.b_ff1, nullptr, 0, nullptr, nullptr, nullptr, R.ff, kFF,
+                               tt * TS, S, kEpiRelu);
+        }
+        barrier();
+      }
+      {  // FF2 + residual
+        float* red = Xs + TS * kFF;
+        for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
+          const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
+          load_rows<kFF>(Xs, R.ff, tt * TS, TS, S, nullptr, nullptr);
+          __syncthreads();
+          linear_item<TS, kFF>(Xs, red, L.w_ff2, kDM, fg * 32, L.b_ff2, R.h, kDM, nullptr, nullptr, nullptr, R.h, kDM,
+                               tt * TS, S, kEpiNone);
+        }
+        barrier();
+      }
+    }
+    {  // last0: Linear(512 -> 128)
+      float* red = Xs + TS * kDM;
+      for (int item = blockIdx.x; item < tiles * (kHid / 32); item += G) {
+        const int tt = item / (kHid / 32), fg = item - tt * (kHid / 32);
+        load_rows<kDM>(Xs, R.h, tt * TS, TS, S, nullptr, nullptr);
+        __syncthreads();
+        linear_item<TS, kDM>(Xs, red, W.w_last0, kHid, fg * 32, W.b_last0, nullptr, 0, nullptr, nullptr, nullptr, R.u, kHid,
+                             tt * TS, S, kEpiNone);
+      }
+      barrier();
+    }
+    {  // tail: one warp per token
+      const int warp_global = blockIdx.x * kDenWarps + (threadIdx.x >> 5);
+      for (int s = warp_global; s < S; s += G * kDenWarps) tail_token(W, R, s, t, t == R.t_lo);
+      barrier();
+    }
+  }
+}
+
+inline size_t denoiser_smem_bytes(int TS, int frames) {
+  size_t lin = (size_t)TS * kFF + (size_t)kDenWarps * TS * 32;                        // X tile + reduction
+  size_t att = (size_t)frames * (kHD + 1) + (size_t)frames * kHD + 2 * kDenWarps * kHD;  // K, V, Q, P
+  return sizeof(float) * (lin > att ? lin : att) + 256;
+}
+
+}  // namespace pdb

@@ -1,0 +1,330 @@
+"""GPU parity tests: the sm_100a path (through the C-ABI library) vs the reference fixtures
+(tests/golden, produced by the reference's own modules) and vs the CPU oracle on seeded inputs.
+
+Tolerances (fp32 end to end; the reference is fp32 too):
+  * denoiser output eps:        |d| <= 3e-5 absolute (values are O(0.1..1); different summation order only)
+  * one DDPM step (teacher-forced): 1e-5 relative to max |x|
+  * Sampson gradient:           2e-4 of max |grad| vs the reference's fp32 autograd, 1e-4 vs the fp64 closed form
+  * valid-match counts / pair-segment indexing / iteration counts / early exits: exact
+  * GGS pose after a five-phase call: 2e-5 of max |pose| (the update is norm-clipped: 1e-4 |pose| per iteration)
+"""
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, matches_from
+from oracle import pose_oracle as po
+from oracle import sampson_f64 as s64
+
+import posediffusion_b200 as pdb
+from posediffusion_b200 import _native
+from posediffusion_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+TRANSFORMER = dict(d_model=512, nhead=4, dim_feedforward=1024, num_encoder_layers=8, dropout=0.1, batch_first=True, norm_first=True)
+FLAGS = ((1, 1, 1), (0, 0, 1), (1, 0, 0), (0, 1, 0))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def golden_state():
+    g = load_golden("denoiser.npz")
+    return syn.random_denoiser_state(int(g["weight_seed"]), float(g["bias_std"]))
+
+
+@pytest.fixture(scope="module")
+def sampler(dev, golden_state):
+    den = pdb.Denoiser(TRANSFORMER=TRANSFORMER)
+    den.load_state_dict(golden_state, strict=True)
+    dif = pdb.GaussianDiffusion()
+    dif.model = den
+    return dif.to(dev)
+
+
+@pytest.fixture(scope="module")
+def ctx(sampler):
+    return sampler.model.native_context()
+
+
+def nan_close(actual, desired, atol):
+    actual, desired = np.asarray(actual, dtype=np.float64), np.asarray(desired, dtype=np.float64)
+    assert np.array_equal(np.isnan(actual), np.isnan(desired))
+    ok = ~np.isnan(desired)
+    np.testing.assert_allclose(actual[ok], desired[ok], rtol=0, atol=atol)
+
+
+# ---------------------------------------------------------------------------------------------------
+# denoiser / sampler
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["b1n5", "b1n20", "b2n20", "b1n80"])
+def test_denoiser_forward_vs_reference(sampler, dev, tag):
+    g = load_golden("denoiser.npz")
+    x, z = torch.from_numpy(g[f"{tag}_x"]).to(dev), torch.from_numpy(g[f"{tag}_z"]).to(dev)
+    t = torch.full((x.shape[0],), int(g[f"{tag}_t"]), dtype=torch.long, device=dev)
+    eps = sampler.model(x, t, z).cpu().numpy()
+    np.testing.assert_allclose(eps, g[f"{tag}_eps"], rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize("t", [99, 50, 11, 10, 9, 0])
+def test_p_sample_teacher_forced_vs_reference(ctx, dev, t):
+    g = load_golden("p_sample.npz")
+    x, noise, z = (torch.from_numpy(g[k]).to(dev) for k in (f"t{t}_x", f"t{t}_noise", "z"))
+    pred, mean, x0 = ctx.p_sample(x, t, z, None if t == 0 else noise)
+    scale = np.abs(g[f"t{t}_x0"]).max()
+    np.testing.assert_allclose(x0.cpu().numpy(), g[f"t{t}_x0"], rtol=0, atol=1e-5 * scale + 3e-5 * abs(float(po.diffusion_schedule()["sqrt_recipm1_alphas_cumprod"][t])))
+    np.testing.assert_allclose(pred.cpu().numpy(), g[f"t{t}_pred"], rtol=0, atol=2e-5 * np.abs(g[f"t{t}_pred"]).max() + 1e-5)
+
+
+def test_loop_ggs_off_vs_reference(sampler, dev):
+    g = load_golden("loop.npz")
+    z, draws = torch.from_numpy(g["z"]).to(dev), torch.from_numpy(g["draws"]).to(dev)
+    pose, trail = sampler.p_sample_loop([1, 5, 9], z, None, 0, draws=draws)
+    ref = g["off_trail"]
+    assert trail.shape == ref.shape
+    # free-running agreement over the first 40 steps, then teacher-forced per step (chaotic with random weights)
+    np.testing.assert_allclose(trail[:41].cpu().numpy(), ref[:41], rtol=0, atol=5e-4 * np.abs(ref[:41]).max())
+    ctx = sampler.model.native_context()
+    for t in (99, 70, 40, 12, 3, 0):
+        k = 99 - t
+        pred, _, _ = ctx.p_sample(torch.from_numpy(ref[k]).to(dev), t, z, None if t == 0 else draws[1 + k])
+        np.testing.assert_allclose(pred.cpu().numpy(), ref[k + 1], rtol=0, atol=3e-5 * np.abs(ref[k + 1]).max() + 1e-5)
+    assert torch.equal(pose, trail[-1])
+
+
+def test_loop_ggs_on_vs_reference(sampler, dev):
+    g = load_golden("loop.npz")
+    m = matches_from(g, "on")
+    cfg = syn.default_ggs_cfg()
+    cfg.update(iter_num=int(g["on_iter_num"]), min_matches=0, verbose=False)
+    cond = partial(pdb.geometry_guided_sampling, matches_dict=m, GGS_cfg=cfg)
+    z, draws = torch.from_numpy(g["z"]).to(dev), torch.from_numpy(g["draws"])
+    slots = torch.cat([draws[:91], torch.zeros(10, *draws.shape[1:])]).to(dev)  # guided steps draw nothing
+    pose, trail = sampler.p_sample_loop([1, 5, 9], z, cond, 10, draws=slots)
+    ref = g["on_trail"]
+    np.testing.assert_allclose(trail[:41].cpu().numpy(), ref[:41], rtol=0, atol=5e-4 * np.abs(ref[:41]).max())
+    assert torch.isfinite(trail).all()
+    # guided steps teacher-forced through the public step API (p_sample + cond_fn)
+    for t in range(9, -1, -1):
+        got, _ = sampler.p_sample(torch.from_numpy(ref[99 - t]).to(dev), t, z, cond_fn=cond, cond_start_step=10)
+        np.testing.assert_allclose(got.cpu().numpy(), ref[100 - t], rtol=0, atol=5e-5 * np.abs(ref[100 - t]).max())
+    # the fused loop and the generic-callable loop agree
+    generic = lambda mean, t: pdb.geometry_guided_sampling(mean, t, m, cfg)
+    pose2, trail2 = sampler.p_sample_loop([1, 5, 9], z, generic, 10, draws=slots)
+    np.testing.assert_allclose(trail2.cpu().numpy(), trail.cpu().numpy(), rtol=0, atol=2e-3 * np.abs(ref).max())
+
+
+def test_rng_draw_order_matches_reference(sampler, dev):
+    """1 + 99 draws unguided, 1 + 90 with start_step 10, consumed in loop order on the device generator."""
+    torch.manual_seed(123)
+    d = sampler.draw_noise((1, 5, 9), dev, 10)
+    torch.manual_seed(123)
+    first = torch.randn(1, 5, 9, device=dev)
+    rest = [torch.randn(1, 5, 9, device=dev) for _ in range(90)]
+    assert torch.equal(d[0], first) and all(torch.equal(d[1 + k], rest[k]) for k in range(90))
+    assert float(d[91:].abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# Sampson error + gradient
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["scene6", "ragged5", "uniform5", "empty5", "diag4", "clamp4"])
+@pytest.mark.parametrize("flags", FLAGS)
+def test_sampson_eval_vs_reference(ctx, dev, tag, flags):
+    g = load_golden("sampson.npz")
+    m = matches_from(g, tag)
+    key = f"{tag}_f{''.join(map(str, flags))}"
+    pm = ctx.pack_matches(m)
+    grad, sc, Fd, Gd = ctx.sampson_eval(pm, torch.from_numpy(g[f"{tag}_pose"]).to(dev), *map(bool, flags), dump=True)
+    grad, sc = grad.cpu().numpy(), sc.cpu().numpy()
+    n_ref = int(g[f"{key}_n_valid"])
+    assert int(sc[1]) == n_ref
+    nan_close(sc[2], g[f"{key}_logged"], 1e-5 * 10)
+    c = s64.sampson_closed_form_f64(g[f"{tag}_pose"], m, *map(bool, flags))
+    # per-segment F' and G against the closed form (segments are runs of equal pairs, in input order)
+    i12 = m["i12"]
+    runs = [0] + [i for i in range(1, len(i12)) if (i12[i] != i12[i - 1]).any()]
+    assert pm.segments == len(runs)
+    frames = m["img_shape"][0]
+    Fd, Gd = Fd.cpu().numpy(), Gd.cpu().numpy()
+    seen = {}
+    for s, r in enumerate(runs):
+        pid = int(i12[r, 0] * frames + i12[r, 1])
+        Fref = c["F"][pid].reshape(-1)
+        np.testing.assert_allclose(Fd[s], Fref, rtol=0, atol=2e-5 * max(np.abs(Fref).max(), 1e-30))
+        seen.setdefault(pid, np.zeros(9))
+        seen[pid] += Gd[s]
+    for pid, Gsum in seen.items():
+        Gref = c["G"][pid].reshape(-1)
+        nan_close(Gsum, Gref, 5e-4 * max(np.nanmax(np.abs(Gref)), 1e-30) if not np.all(np.isnan(Gref)) else 0)
+    if n_ref == 0:
+        return
+    ref = g[f"{key}_grad"]
+    gmax = np.nanmax(np.abs(ref))
+    np.testing.assert_allclose(sc[0], g[f"{key}_loss"], rtol=2e-5)
+    nan_close(grad, ref, 2e-4 * gmax)
+    nan_close(grad, c["grad"], 1e-4 * gmax)
+    assert np.array_equal(grad == 0, ref == 0)
+
+
+@pytest.mark.parametrize("frames,per_pair,ragged", [(20, 256, False), (12, 100, True), (3, 5000, False), (40, 37, False)])
+def test_sampson_eval_vs_oracle_seeded(ctx, dev, frames, per_pair, ragged):
+    """Sizes the fixtures do not hold: many CTAs per problem, multi-chunk segment spans, ragged pairs."""
+    m, gt, start = syn.scene_matches(frames, per_pair, seed=frames, ragged=ragged)
+    pm = ctx.pack_matches(m)
+    assert pm.m_total == len(m["kp1"])
+    grad, sc, _, _ = ctx.sampson_eval(pm, torch.from_numpy(start).to(dev))
+    prep = po.prepare_matches(m)
+    pose = torch.from_numpy(start)[None].clone().requires_grad_(True)
+    with torch.enable_grad():
+        valid, logged = po.sampson_terms(pose, prep)
+        valid.mean().backward()
+    c = s64.sampson_closed_form_f64(start, m)
+    assert abs(int(sc[1].item()) - len(valid)) <= 2 and abs(int(sc[1].item()) - c["n_valid"]) <= 2
+    gmax = np.abs(c["grad"]).max()
+    np.testing.assert_allclose(grad.cpu().numpy(), c["grad"], rtol=0, atol=3e-4 * gmax)
+    np.testing.assert_allclose(grad.cpu().numpy(), pose.grad[0].numpy(), rtol=0, atol=5e-4 * gmax)
+    np.testing.assert_allclose(sc[2].item(), float(logged), rtol=1e-4)
+
+
+def test_sampson_properties_at_full_size(ctx, dev):
+    """BASELINE config 3 size (N=20, 380 ordered pairs x 2048 = 778 240 matches): size-independent properties."""
+    frames, per_pair = 20, 2048
+    m, gt, start = syn.scene_matches(frames, per_pair, seed=77)
+    pose = torch.from_numpy(start).to(dev)
+    pm = ctx.pack_matches(m)
+    assert (pm.m_total, pm.segments, pm.rounds) == (380 * 2048, 380, 380 * 64)
+    g1, s1, _, _ = ctx.sampson_eval(pm, pose)
+    # (a) run-to-run: identical counts, gradient equal up to atomics ordering
+    g2, s2, _, _ = ctx.sampson_eval(pm, pose)
+    assert s1[1].item() == s2[1].item()
+    gmax = g1.abs().max().item()
+    assert (g1 - g2).abs().max().item() <= 2e-5 * gmax
+    # (b) permuting the pair order leaves the mean gradient unchanged
+    order = np.random.default_rng(0).permutation(380)
+    idx = (order[:, None] * per_pair + np.arange(per_pair)[None]).reshape(-1)
+    mp = {"kp1": m["kp1"][idx], "kp2": m["kp2"][idx], "i12": m["i12"][idx], "img_shape": m["img_shape"]}
+    g3, s3, _, _ = ctx.sampson_eval(ctx.pack_matches(mp), pose)
+    assert s3[1].item() == s1[1].item()
+    assert (g1 - g3).abs().max().item() <= 5e-5 * gmax
+    # (c) duplicating every match leaves mean loss / gradient unchanged and doubles the valid count
+    md = {k: (np.concatenate([v, v]) if k != "img_shape" else v) for k, v in m.items()}
+    g4, s4, _, _ = ctx.sampson_eval(ctx.pack_matches(md), pose)
+    assert s4[1].item() == 2 * s1[1].item()
+    assert (g1 - g4).abs().max().item() <= 5e-5 * gmax and abs(s4[0].item() - s1[0].item()) <= 1e-4 * s1[0].item()
+    # (d) detached blocks: flags partition the full gradient exactly
+    gR, _, _, _ = ctx.sampson_eval(pm, pose, True, False, False)
+    gT, _, _, _ = ctx.sampson_eval(pm, pose, False, True, False)
+    gF, _, _, _ = ctx.sampson_eval(pm, pose, False, False, True)
+    assert (gR[:, :3] == 0).all() and (gR[:, 7:] == 0).all() and (gT[:, 3:] == 0).all() and (gF[:, :7] == 0).all()
+    assert ((gR + gT + gF) - g1).abs().max().item() <= 5e-5 * gmax
+    # (e) noise-free correspondences have (near) zero error at the ground-truth pose
+    m0, gt0, _ = syn.scene_matches(frames, 256, seed=78, pixel_noise=0.0)
+    _, s0, _, _ = ctx.sampson_eval(ctx.pack_matches(m0), torch.from_numpy(gt0).to(dev))
+    assert s0[1].item() == 380 * 256 and s0[0].item() < 1e-4
+
+
+def test_matches_pack_validation(ctx):
+    m = syn.uniform_matches(4, 8, seed=1)
+    bad = dict(m)
+    bad["i12"] = m["i12"].copy()
+    bad["i12"][5, 1] = 4
+    with pytest.raises(ValueError):
+        ctx.pack_matches(bad)
+    empty = {"kp1": np.zeros((0, 2)), "kp2": np.zeros((0, 2)), "i12": np.zeros((0, 2), np.int64), "img_shape": (4, 3, 224, 224)}
+    pm = ctx.pack_matches(empty)
+    assert (pm.m_total, pm.segments, pm.rounds) == (0, 0, 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# geometry-guided sampling
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["scene5", "scene8"])
+def test_ggs_five_phases_vs_reference(ctx, dev, tag):
+    g = load_golden("ggs.npz")
+    cfg = syn.default_ggs_cfg()
+    cfg["iter_num"] = int(g["iter_num"])
+    m = matches_from(g, tag)
+    pose = torch.from_numpy(g[f"{tag}_pose"])[None].to(dev).clone()
+    stats = ctx.ggs([ctx.pack_matches(m)], pose, cfg)
+    row = _native.stats_to_numpy(stats)[0]
+    ref = g[f"{tag}_out"]
+    np.testing.assert_allclose(pose[0].cpu().numpy(), ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    n = cfg["iter_num"]
+    assert list(row["iters"]) == [2 * n, n, n, n, 2 * n] and int(row["dropped"].sum()) == int(g[f"{tag}_drops"])
+    np.testing.assert_allclose(row["sampson"], g[f"{tag}_log"], rtol=2e-4)
+
+
+def test_ggs_early_exit_vs_reference(ctx, dev, capsys):
+    g = load_golden("ggs.npz")
+    cfg = syn.default_ggs_cfg()
+    cfg["iter_num"] = int(g["iter_num"])
+    m = matches_from(g, "drop")
+    pose = torch.from_numpy(g["drop_pose"])[None].to(dev).clone()
+    out = pdb.geometry_guided_sampling(pose, 3, m, cfg)  # the public drop-in, printing like the reference
+    text = capsys.readouterr().out
+    assert text.count("Drop this pair because of insufficient valid matches") == int(g["drop_drops"]) == 5
+    assert text.count("t=03 | sampson=") == 5
+    assert np.array_equal(out[0].cpu().numpy(), g["drop_out"])  # no update at all
+
+
+def test_ggs_long_run_vs_oracle(ctx, dev):
+    """Default iteration counts (700 inner iterations) on a consistent scene: agreement with the CPU oracle and descent."""
+    m, gt, start = syn.scene_matches(6, 128, seed=5)
+    cfg = syn.default_ggs_cfg()
+    pose = torch.from_numpy(start)[None].to(dev).clone()
+    stats = _native.stats_to_numpy(ctx.ggs([ctx.pack_matches(m)], pose, cfg))[0]
+    log = []
+    want = po.geometry_guided_sampling(torch.from_numpy(start)[None], 5, m, cfg, log=log)
+    assert list(stats["iters"]) == [e["iters"] for e in log] == [200, 100, 100, 100, 200]
+    np.testing.assert_allclose(pose[0].cpu().numpy(), want[0].numpy(), rtol=0, atol=1e-3 * np.abs(want).max().item())
+    np.testing.assert_allclose(stats["sampson"], [e["sampson"] for e in log], rtol=2e-2)
+    assert stats["sampson"][-1] < stats["sampson"][0]
+
+
+def test_ggs_batch_equals_singles(ctx, dev):
+    """B independent sequences in one launch == B single launches (the path shards over sequences)."""
+    cfg = syn.default_ggs_cfg()
+    cfg["iter_num"] = 5
+    sets = [syn.scene_matches(7, 64 + 16 * s, seed=40 + s) for s in range(3)]
+    packs = [ctx.pack_matches(s[0]) for s in sets]
+    starts = torch.stack([torch.from_numpy(s[2]) for s in sets]).to(dev)
+    batch = starts.clone()
+    ctx.ggs(packs, batch, cfg)
+    for i in range(3):
+        single = starts[i : i + 1].clone()
+        ctx.ggs([packs[i]], single, cfg)
+        np.testing.assert_allclose(batch[i].cpu().numpy(), single[0].cpu().numpy(), rtol=0, atol=1e-5 * single.abs().max().item())
+
+
+def test_batched_denoiser_equals_singles(sampler, dev):
+    x = torch.randn(3, 20, 9, device=dev)
+    z = torch.randn(3, 20, 384, device=dev)
+    t = torch.full((3,), 42, dtype=torch.long, device=dev)
+    full = sampler.model(x, t, z)
+    for i in range(3):
+        one = sampler.model(x[i : i + 1].contiguous(), t[:1], z[i : i + 1].contiguous())
+        np.testing.assert_allclose(full[i].cpu().numpy(), one[0].cpu().numpy(), rtol=0, atol=1e-6)
+
+
+def test_pose_diffusion_model_api(dev, golden_state):
+    model = pdb.PoseDiffusionModel(
+        pose_encoding_type="absT_quaR_logFL", IMAGE_FEATURE_EXTRACTOR=None,
+        DIFFUSER={"_target_": "models.GaussianDiffusion", "beta_schedule": "custom"},
+        DENOISER={"_target_": "models.Denoiser", "TRANSFORMER": dict(TRANSFORMER, _target_="models.TransformerEncoderWrapper")},
+    ).to(dev)
+    model.diffuser.model.load_state_dict(golden_state, strict=True)
+    z = torch.randn(1, 6, 384, device=dev)
+    torch.manual_seed(0)
+    out = model(z=z, training=False)
+    cams = out["pred_cameras"]
+    assert len(cams) == 6 and torch.isfinite(cams.R).all() and torch.isfinite(cams.T).all()
+    torch.manual_seed(0)
+    again = model(z=z, training=False)["pred_cameras"]
+    assert torch.equal(cams.T, again.T)  # deterministic given the seed (GGS off: no atomics on the path)
