@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- diffusion steps/sec of the PoseDiffusion sampling hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg5]
+    (N > 1: launched by torchrun, one rank per GPU over NCCL)
+
+A bench "step" is one full p_sample_loop of the workload: T = 100 diffusion steps of one 20-frame sequence per GPU,
+the last 10 of them guided (7 000 inner Sampson/GGS iterations over 778 240 matches).  `value` counts diffusion
+steps: world * sequences_per_gpu * 100 * K / (max-over-ranks device time of the K timed loops).
+
+Output: ONE JSON line on rank 0 (see the contract in the task statement): value (inputs resident in HBM),
+e2e (host buffers through the C-ABI call, H2D/D2H and match packing inside the timed region), roofline of the
+dominant kernel (GGS/Sampson, HBM-bound, algorithmic 16 B per match-evaluation), cpu_baseline (the CPU oracle
+port on this box's host cores, bounded sample, extrapolated), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+T_STEPS = 100
+WORKLOADS = {
+    # name: (frames, matches per ordered pair or 0 for GGS off, description)
+    "cfg3": (20, 2048, "BASELINE configs[2]: 1 sequence x 20 frames per GPU, T=100, GGS on (start_step 10, 700 inner iters/step), "
+                      "M=2048 uniform-random matches for each of the 380 ordered pairs (778240 matches)"),
+    "cfg2": (20, 0, "BASELINE configs[1]: 1 sequence x 20 frames per GPU, T=100, GGS off (denoiser-only path)"),
+    "cfg5": (80, 4096, "BASELINE configs[4]: 1 sequence x 80 frames, T=100, GGS on, M=4096 x 6320 ordered pairs (25886720 matches)"),
+}
+ALGO_BYTES_PER_MATCH_EVAL = 16  # kp1.xy + kp2.xy as fp32
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        load = [v for v in sm if mx and v > 0.5 * mx[0]] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is Python and does not exist on the GPU box; oracle/pose_oracle.py
+# restates it operator for operator in PyTorch-CPU, see its header).  Bounded sample, extrapolated.
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_run(frames: int, per_pair: int, seed: int, threads: int, budget_s: float):
+    from functools import partial
+
+    from oracle import pose_oracle as po
+    from posediffusion_b200 import synthetic as syn
+
+    torch.set_num_threads(threads)
+    state = syn.random_denoiser_state(seed)
+    net = po.build_denoiser(state)
+    sched = po.diffusion_schedule()
+    z = syn.random_features(1, frames, seed)
+    draws = syn.predraw_noise(1, frames, seed=seed)
+    with torch.no_grad():
+        po.p_sample(net, sched, draws[0], 99, z, draws[1])  # warm-up
+    t0 = time.perf_counter()
+    pose, _ = po.p_sample_loop(net, sched, z, draws, None, 0)  # 100 denoiser + DDPM steps
+    t_denoise = time.perf_counter() - t0
+    sample = f"100 denoiser steps ({t_denoise:.2f} s)"
+    inner_total, t_inner, n_inner = 0, 0.0, 0
+    if per_pair > 0:
+        m = syn.uniform_matches(frames, per_pair, seed=seed)
+        prep = po.prepare_matches(m)
+        cfg = syn.default_ggs_cfg()
+        inner_total = cfg["start_step"] * 7 * cfg["iter_num"]  # 10 guided steps x (2+1+1+1+2) x 100
+        # time all-parameter GGS iterations (every phase costs the same forward + backward) until the budget is spent
+        mean = pose.clone()
+        po.ggs_phase(mean, prep, iter_num=1, min_matches=0)  # warm-up (2 iterations)
+        t_start = time.perf_counter()
+        while time.perf_counter() - t_start < budget_s:
+            t1 = time.perf_counter()
+            mean = po.ggs_phase(mean, prep, iter_num=1, min_matches=0)  # all flags on -> iter_num doubles: 2 iterations
+            t_inner += time.perf_counter() - t1
+            n_inner += 2
+        sample += f" + {n_inner} of {inner_total} inner GGS iterations ({t_inner:.2f} s), extrapolated"
+    wall = t_denoise + (inner_total * t_inner / n_inner if n_inner else 0.0)
+    return {"steps_per_s": T_STEPS / wall, "wall_s_full": wall, "sample": sample, "threads": threads}
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--seqs-per-gpu", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU GGS iterations in the bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    frames, per_pair, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        res = cpu_reference_run(frames, per_pair, args.seed, threads, args.cpu_budget * max(1, args.steps))
+        line = {
+            "impl": "reference", "metric": "diffusion steps/sec (20-frame seq, GGS on)", "value": res["steps_per_s"],
+            "unit": "diffusion steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * res["wall_s_full"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "timesteps": T_STEPS},
+            "cpu_baseline": {"value": res["steps_per_s"], "unit": "diffusion steps/s", "cores": res["threads"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["steps_per_s"], "unit": "diffusion steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------
+    import posediffusion_b200 as pdb
+    from posediffusion_b200 import _native
+    from posediffusion_b200 import synthetic as syn
+    from posediffusion_b200.distributed import gather_poses, init_from_env, sequence_seed, shard_range
+
+    rank, world, local = init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B = args.seqs_per_gpu
+    total_seqs = B * world
+    lo, hi = shard_range(total_seqs, rank, world)
+
+    den = pdb.Denoiser(TRANSFORMER=dict(d_model=512, nhead=4, dim_feedforward=1024, num_encoder_layers=8, dropout=0.1,
+                                        batch_first=True, norm_first=True))
+    den.load_state_dict(syn.random_denoiser_state(args.seed), strict=True)
+    den = den.to(dev)
+    ctx = den.native_context()
+    cfg = syn.default_ggs_cfg()
+    cfg["verbose"] = False
+    start_step = cfg["start_step"] if per_pair else 0
+
+    # per-sequence synthetic inputs keyed by the GLOBAL sequence index (world-size invariant results)
+    z_host = torch.cat([syn.random_features(1, frames, sequence_seed(args.seed, g)) for g in range(lo, hi)]).pin_memory()
+    draws_host = torch.cat([syn.predraw_noise(1, frames, seed=sequence_seed(args.seed, g)) for g in range(lo, hi)], dim=1).contiguous().pin_memory()
+    match_dicts = [syn.uniform_matches(frames, per_pair, seed=sequence_seed(args.seed, g)) for g in range(lo, hi)] if per_pair else None
+    z_dev, draws_dev = z_host.to(dev), draws_host.to(dev)
+    problems = [ctx.pack_matches(m) for m in match_dicts] if per_pair else None
+    m_total = problems[0].m_total if per_pair else 0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_loop():
+        pose, _, _ = ctx.sample_loop(z_dev, draws_dev, problems, cfg if per_pair else None, start_step, want_trail=False, want_stats=False)
+        return pose
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        pose = one_loop()
+    sync_all()
+
+    # ---- timed region: K loops, L2 flushed between them, CUDA events on the launch stream ----
+    ctx.profile(True)
+    ctx.profile_read()
+    launches0 = ctx.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    with ClockSampler(local) as clocks:
+        sync_all()
+        for k in range(args.steps):
+            flush.zero_()
+            starts[k].record()
+            pose = one_loop()
+            full = gather_poses(pose, total_seqs)  # the path's only collective (no-op at world 1)
+            stops[k].record()
+        sync_all()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    ggs_ms, ggs_n, den_ms, den_n = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launch_count - launches0
+    t_ms = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+    dev_ms_max = float(t_ms.item())
+    value = total_seqs * T_STEPS * args.steps / (dev_ms_max / 1000.0)
+
+    # ---- end to end through the C-ABI host-buffer call: pack matches (host pass + H2D), H2D z/draws, D2H pose ----
+    pose_host = torch.empty(B, frames, 9).pin_memory()
+    z_np, draws_np, pose_np = z_host.numpy(), draws_host.numpy(), pose_host.numpy()
+
+    def one_e2e():
+        probs = [ctx.pack_matches(m) for m in match_dicts] if per_pair else None
+        ctx.sample_loop_host(z_np, draws_np, probs, cfg if per_pair else None, start_step, pose_np)
+
+    one_e2e()
+    sync_all()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_e2e()
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - e0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = total_seqs * T_STEPS * args.steps / float(e2e_s.item())
+    h2d = z_host.numel() * 4 + draws_host.numel() * 4 + (B * m_total * 16 if per_pair else 0)
+    d2h = pose_host.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return 0
+
+    peak, peak_src = read_peaks()
+    line = {
+        "metric": "diffusion steps/sec (20-frame seq, GGS on)" if args.workload == "cfg3" else f"diffusion steps/sec ({args.workload})",
+        "value": value, "unit": "diffusion steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "sequences_per_gpu": B, "timesteps": T_STEPS,
+                   "parallelism": f"sequences sharded over {world} GPU(s), final all-gather of poses only",
+                   "l2": "flushed between timed loops (256 MiB write); within a loop the 12.45 MB match set is deliberately L2-resident",
+                   "weights": "random init (reference init law), z ~ N(0,1), uniform-random correspondences"},
+        "e2e": {"value": e2e_value, "unit": "diffusion steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "note": "C-ABI pdb_matches_pack + pdb_sample_loop_host with pinned host buffers; reference-format float64/int64 "
+                        "matches are converted on the host (48 B/match read) then uploaded as 16 B/match"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "wall_s_timed_region": wall,
+        "kernel_ms_per_loop": {"ggs": ggs_ms / args.steps, "denoiser": den_ms / args.steps, "ggs_launches": ggs_n // args.steps,
+                               "denoiser_launches": den_n // args.steps},
+    }
+    if per_pair and ggs_n:
+        inner_per_launch = 7 * cfg["iter_num"]
+        algo_bytes = ALGO_BYTES_PER_MATCH_EVAL * m_total * inner_per_launch * B
+        achieved = algo_bytes / (ggs_ms / ggs_n / 1000.0) / 1e9
+        line["roofline"] = {
+            "kernel": "ggs_entry<false> (fused Sampson error+gradient, 700 inner iterations per launch)", "bound": "hbm",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": ggs_ms / ggs_n,
+            "note": "algorithmic bytes = 16 B x matches x inner iterations; at this size the match set (12.45 MB) is L2-resident, "
+                    "so DRAM traffic is far below the algorithmic bytes by design (cfg5, 414 MB/iteration, is the HBM-streaming case)",
+        }
+    if not args.no_cpu_baseline:
+        threads = min(os.cpu_count() or 1, 32)
+        res = cpu_reference_run(frames, per_pair, args.seed, threads, args.cpu_budget)
+        line["cpu_baseline"] = {"value": res["steps_per_s"], "unit": "diffusion steps/s", "cores": res["threads"], "kind": "port",
+                                "sample": res["sample"], "wall_s_full_extrapolated": res["wall_s_full"]}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -81,6 +81,12 @@ int pdb_device_info(const pdb_context* ctx, int32_t* sm_count, int32_t* cc_major
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 int64_t pdb_launch_count(const pdb_context* ctx);
 
+/* Kernel timing for bench.py's roofline line: when enabled, every GGS / denoiser launch is bracketed by CUDA
+ * events on its own stream; pdb_profile_read synchronises those events and returns the summed device time (ms)
+ * and launch counts since the last read. */
+int pdb_profile_enable(pdb_context* ctx, int32_t on);
+int pdb_profile_read(pdb_context* ctx, double* ggs_ms, int64_t* ggs_launches, double* denoiser_ms, int64_t* denoiser_launches);
+
 /* DDPM schedule exactly as GaussianDiffusion.init_diff_hyper builds it (models/gaussian_diffuser.py:136-187;
  * "custom" = float64 linspace(beta_1, beta_T, 100), cumprod, cast to float32).  HOST-ONLY helper, needs no GPU:
  * out[100][8] = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,

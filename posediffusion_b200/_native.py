@@ -62,6 +62,8 @@ EXPORTS = {
     "pdb_last_error": (C.c_char_p, [C.c_void_p]),
     "pdb_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pdb_launch_count": (C.c_int64, [C.c_void_p]),
+    "pdb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pdb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pdb_schedule_table": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "pdb_denoiser_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "pdb_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -187,6 +189,15 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.pdb_launch_count(self.handle))
+
+    def profile(self, on: bool):
+        self._ok(self.lib.pdb_profile_enable(self.handle, int(on)), "pdb_profile_enable")
+
+    def profile_read(self):
+        """(ggs_ms, ggs_launches, denoiser_ms, denoiser_launches) since the last read; synchronises."""
+        a, b, c, d = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
+        self._ok(self.lib.pdb_profile_read(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "pdb_profile_read")
+        return a.value, b.value, c.value, d.value
 
     def sm_count(self) -> int:
         sm, a, b = C.c_int32(), C.c_int32(), C.c_int32()

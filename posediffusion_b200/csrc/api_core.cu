@@ -82,6 +82,34 @@ int pdb_device_info(const pdb_context* c, int32_t* sm_count, int32_t* cc_major, 
   return PDB_OK;
 }
 
+int pdb_profile_enable(pdb_context* c, int32_t on) {
+  if (!c) return PDB_ERR_INVALID;
+  reinterpret_cast<Context*>(c)->profiling = on != 0;
+  return PDB_OK;
+}
+
+int pdb_profile_read(pdb_context* c, double* ggs_ms, int64_t* ggs_launches, double* den_ms, int64_t* den_launches) {
+  if (!c) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  double ms[2] = {0.0, 0.0};
+  int64_t n[2] = {0, 0};
+  for (auto& t : ctx->timed) {
+    PDB_CUDA(ctx, cudaEventSynchronize(t.b));
+    float dt = 0.f;
+    PDB_CUDA(ctx, cudaEventElapsedTime(&dt, t.a, t.b));
+    ms[t.kind] += dt;
+    n[t.kind] += 1;
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  ctx->timed.clear();
+  if (ggs_ms) *ggs_ms = ms[0];
+  if (ggs_launches) *ggs_launches = n[0];
+  if (den_ms) *den_ms = ms[1];
+  if (den_launches) *den_launches = n[1];
+  return PDB_OK;
+}
+
 int64_t pdb_launch_count(const pdb_context* c) { return c ? reinterpret_cast<const Context*>(c)->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,10 +235,10 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   if (cpp > want) cpp = (int)want;
   P.ctas_per_problem = cpp;
   const size_t smem = ggs_smem_bytes(max_frames);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[kEval]) {
-    PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    attr_set[kEval] = true;
+  static size_t attr_bytes = 0;  // per instantiation
+  if (smem > attr_bytes) {
+    PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cpp * nprob);
@@ -222,7 +250,10 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ggs_entry<kEval>, batch, P));
+  {
+    ScopedTimer timer(ctx, st, 0);
+    PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ggs_entry<kEval>, batch, P));
+  }
   ctx->launches += 1;
   return PDB_OK;
 }

@@ -96,10 +96,10 @@ template <int TS>
 int launch_denoiser(Context* ctx, const DenoiserRun& run, int grid, cudaStream_t st) {
   const size_t smem = denoiser_smem_bytes(TS, run.frames);
   if (smem > ctx->smem_optin) return ctx->fail(PDB_ERR_LIMIT, "denoiser needs %zu B shared memory", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PDB_CUDA(ctx, cudaFuncSetAttribute(denoiser_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    attr_set = true;
+  static size_t attr_bytes = 0;  // static shared memory counts against the opt-in limit: ask for what we use
+  if (smem > attr_bytes) {
+    PDB_CUDA(ctx, cudaFuncSetAttribute(denoiser_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -111,7 +111,10 @@ int launch_denoiser(Context* ctx, const DenoiserRun& run, int grid, cudaStream_t
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, denoiser_kernel<TS>, ctx->weights->dev, run));
+  {
+    ScopedTimer timer(ctx, st, 1);
+    PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, denoiser_kernel<TS>, ctx->weights->dev, run));
+  }
   ctx->launches += 1;
   return PDB_OK;
 }

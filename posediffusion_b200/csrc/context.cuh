@@ -27,6 +27,10 @@ struct Context {
   DenoiserWeights* weights = nullptr;
   void* den_ws = nullptr;
   size_t den_ws_bytes = 0;
+  // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser
+  bool profiling = false;
+  struct Timed { cudaEvent_t a, b; int kind; };
+  std::vector<Timed> timed;
   // staging for the host-buffer entry point
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -59,6 +63,16 @@ struct Matches {
     if (err__ != cudaSuccess)                                                                        \
       return (ctx)->fail(PDB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
   } while (0)
+
+struct ScopedTimer {  // records an event pair around a launch when profiling is on
+  Context* ctx; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int kind;
+  ScopedTimer(Context* c, cudaStream_t s, int k) : ctx(c), st(s), kind(k) {
+    if (ctx->profiling) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+  }
+  ~ScopedTimer() {
+    if (a) { cudaEventRecord(b, st); ctx->timed.push_back({a, b, kind}); }
+  }
+};
 
 inline int ensure_buffer(Context* ctx, void** ptr, size_t* have, size_t need) {
   if (*have >= need) return PDB_OK;

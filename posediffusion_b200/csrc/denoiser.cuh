@@ -216,7 +216,7 @@ __device__ __forceinline__ void attention_item(float* __restrict__ smem, const f
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int KP = kHD + 1;  // padded key rows: lane = key index reads are conflict free
   float* Ks = smem;                 // [N][129]
-  float* Vs = Ks + N * KP;          // [N][128]
+  float* Vs = Ks + ((N * KP + 3) & ~3);  // [N][128], 16-byte aligned
   float* Qs = Vs + N * kHD;         // [warps][128]
   float* Ps = Qs + kDenWarps * kHD; // [warps][128]
   const float* base = qkv + (size_t)seq * N * (3 * kDM) + head * kHD;
@@ -438,7 +438,7 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
 
 inline size_t denoiser_smem_bytes(int TS, int frames) {
   size_t lin = (size_t)TS * kFF + (size_t)kDenWarps * TS * 32;                        // X tile + reduction
-  size_t att = (size_t)frames * (kHD + 1) + (size_t)frames * kHD + 2 * kDenWarps * kHD;  // K, V, Q, P
+  size_t att = (size_t)frames * (kHD + 1) + 4 + (size_t)frames * kHD + 2 * kDenWarps * kHD;  // K, V, Q, P
   return sizeof(float) * (lin > att ? lin : att) + 256;
 }
 
