@@ -87,6 +87,10 @@ int64_t pdb_launch_count(const pdb_context* ctx);
 int pdb_profile_enable(pdb_context* ctx, int32_t on);
 int pdb_profile_read(pdb_context* ctx, double* ggs_ms, int64_t* ggs_launches, double* denoiser_ms, int64_t* denoiser_launches);
 
+/* Debug probe (not part of the reference surface): per-CTA cycle sums of the GGS kernel's stages
+ * out[cta][8] = {stage0, stage1+2a, stage2b, barrier, stage3, iterations, 0, 0}; enable != 0 arms it for single-sequence calls. */
+int pdb_debug_ggs_clocks(pdb_context* ctx, int32_t enable, int64_t* out, int32_t max_ctas);
+
 /* DDPM schedule exactly as GaussianDiffusion.init_diff_hyper builds it (models/gaussian_diffuser.py:136-187;
  * "custom" = float64 linspace(beta_1, beta_T, 100), cumprod, cast to float32).  HOST-ONLY helper, needs no GPU:
  * out[100][8] = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,

@@ -64,6 +64,7 @@ EXPORTS = {
     "pdb_launch_count": (C.c_int64, [C.c_void_p]),
     "pdb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "pdb_debug_ggs_clocks": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "pdb_schedule_table": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "pdb_denoiser_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "pdb_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -198,6 +199,11 @@ class Context:
         a, b, c, d = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
         self._ok(self.lib.pdb_profile_read(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "pdb_profile_read")
         return a.value, b.value, c.value, d.value
+
+    def ggs_clocks(self, enable: bool = True, read: bool = False):
+        out = np.zeros((256, 8), dtype=np.int64) if read else None
+        self._ok(self.lib.pdb_debug_ggs_clocks(self.handle, int(enable), out.ctypes.data if read else None, 256), "pdb_debug_ggs_clocks")
+        return out
 
     def sm_count(self) -> int:
         sm, a, b = C.c_int32(), C.c_int32(), C.c_int32()

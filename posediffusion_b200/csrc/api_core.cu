@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kGgsThreads, 1)
 ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P);
 
 size_t ggs_ws_per_problem(int frames) {
-  size_t bytes = 16 + sizeof(float) * 3 * (frames * 7 + kAccTail);  // {bar, cnt[3]} + 3 accumulators
+  size_t bytes = 128 + sizeof(float) * 3 * (size_t)(frames * 7 + kAccTail) * kAccPad;  // {bar, cnt[3]} + 3 padded accumulators
   return (bytes + 255) / 256 * 256;
 }
 }  // namespace
@@ -107,6 +107,29 @@ int pdb_profile_read(pdb_context* c, double* ggs_ms, int64_t* ggs_launches, doub
   if (ggs_launches) *ggs_launches = n[0];
   if (den_ms) *den_ms = ms[1];
   if (den_launches) *den_launches = n[1];
+  return PDB_OK;
+}
+
+// Debug probe: per-CTA cycle sums of the GGS stages {stage0, stage1+2a, stage2b, barrier, stage3, iterations}.
+int pdb_debug_ggs_clocks(pdb_context* c, int32_t enable, int64_t* out, int32_t max_ctas) {
+  if (!c) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (enable && !ctx->ggs_clock) {
+    ctx->ggs_clock_ctas = ctx->sm_count;
+    PDB_CUDA(ctx, cudaMalloc(&ctx->ggs_clock, sizeof(long long) * 8 * ctx->ggs_clock_ctas));
+    PDB_CUDA(ctx, cudaMemset(ctx->ggs_clock, 0, sizeof(long long) * 8 * ctx->ggs_clock_ctas));
+  }
+  if (out && ctx->ggs_clock) {
+    PDB_CUDA(ctx, cudaDeviceSynchronize());
+    const int n = max_ctas < ctx->ggs_clock_ctas ? max_ctas : ctx->ggs_clock_ctas;
+    PDB_CUDA(ctx, cudaMemcpy(out, ctx->ggs_clock, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost));
+    PDB_CUDA(ctx, cudaMemset(ctx->ggs_clock, 0, sizeof(long long) * 8 * ctx->ggs_clock_ctas));
+  }
+  if (!enable && ctx->ggs_clock) {
+    cudaFree(ctx->ggs_clock);
+    ctx->ggs_clock = nullptr;
+  }
   return PDB_OK;
 }
 
@@ -234,7 +257,13 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   if (want < 1) want = 1;
   if (cpp > want) cpp = (int)want;
   P.ctas_per_problem = cpp;
-  const size_t smem = ggs_smem_bytes(max_frames);
+  // shared-memory match cache: everything beyond the fixed per-frame state, in rounds of 512 B
+  const size_t fixed = ggs_smem_fixed_bytes(max_frames);
+  const size_t budget = ctx->smem_optin > fixed + 1024 ? ctx->smem_optin - fixed - 1024 : 0;
+  const long long rounds_per_cta = (max_rounds + cpp - 1) / cpp + 1;
+  const bool resident = (size_t)rounds_per_cta * 512 <= budget;
+  P.resident_rounds = resident ? (int)rounds_per_cta : 0;
+  const size_t smem = fixed + (resident ? (size_t)rounds_per_cta * 512 : 0);
   static size_t attr_bytes = 0;  // per instantiation
   if (smem > attr_bytes) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -312,8 +341,9 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* po
       p.pose = pose_dev + (size_t)(b0 + i) * N * 9;
       p.bar = reinterpret_cast<unsigned*>(ws);
       p.gcnt = reinterpret_cast<int*>(ws + 4);
-      p.gacc = reinterpret_cast<float*>(ws + 16);
+      p.gacc = reinterpret_cast<float*>(ws + 128);
       p.stats = stats_dev ? stats_dev + (b0 + i) : nullptr;
+      p.dbg_clock = (ctx->ggs_clock && batch == 1) ? ctx->ggs_clock : nullptr;
       ws += ggs_ws_per_problem(m->frames);
       max_rounds = max_rounds > m->rounds ? max_rounds : m->rounds;
     }
@@ -370,7 +400,7 @@ int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_de
   p.pose = const_cast<float*>(pose_dev);  // eval mode never writes the pose
   p.bar = reinterpret_cast<unsigned*>(ws);
   p.gcnt = reinterpret_cast<int*>(ws + 4);
-  p.gacc = reinterpret_cast<float*>(ws + 16);
+  p.gacc = reinterpret_cast<float*>(ws + 128);
   p.dbg_grad = grad_dev;
   p.dbg_scalars = scalars_dev;
   p.dbg_F = F_dev;

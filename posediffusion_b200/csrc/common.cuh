@@ -95,4 +95,21 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target
   __syncthreads();
 }
 
+// The same barrier executed by ONE warp per CTA (the rest of the CTA waits at a later __syncthreads).
+// All 32 lanes may have issued global atomics before; __syncwarp orders them before lane 0's release.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void warp_group_barrier(unsigned* counter, unsigned target) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    red_release_add_u32(counter, 1u);
+    while (ld_acquire_u32(counter) < target) {
+    }
+  }
+  __syncwarp();
+}
+
 }  // namespace pdb

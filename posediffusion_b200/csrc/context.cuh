@@ -27,6 +27,9 @@ struct Context {
   DenoiserWeights* weights = nullptr;
   void* den_ws = nullptr;
   size_t den_ws_bytes = 0;
+  // stage timing probe of the GGS kernel (debug): [ctas][8] cycle sums
+  long long* ggs_clock = nullptr;
+  int ggs_clock_ctas = 0;
   // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser
   bool profiling = false;
   struct Timed { cudaEvent_t a, b; int kind; };

@@ -240,4 +240,61 @@ PDB_HD int sampson_match(const float4 pt, const float* F, bool inb, float smax, 
   return valid ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// "K-folded" formulation used by the kernels: with At_n = K^-T A_n and Rt_n = K^-T R_n (per frame),
+//   F'_{ab} = K^-T M K^-1 = -(At_a Rt_b^T + Rt_a At_b^T),
+// so every entry of F' is 6 FMAs of per-frame terms and the per-pair adjoint needs no K at all:
+//   gAt_a -= G Rt_b ;  gRt_a -= G At_b ;  gRt_b -= G^T At_a ;  gAt_b -= G^T Rt_a.
+// The intrinsics' adjoint moves to the (few) frames:  gA = K^-1 gAt, gR = K^-1 gRt, gK^-1 += A gAt^T + R gRt^T.
+// ---------------------------------------------------------------------------------------------
+PDB_HD void frame_tilde(const float* X, const float* kin, float* Xt) {  // Xt = K^-T X
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    Xt[0 + j] = kin[0] * X[0 + j];
+    Xt[3 + j] = kin[1] * X[3 + j];
+    Xt[6 + j] = kin[2] * X[0 + j] + kin[3] * X[3 + j] + X[6 + j];
+  }
+}
+
+PDB_HD float pair_F_entry(const float* At_a, const float* Rt_a, const float* At_b, const float* Rt_b, int i, int j) {
+  float acc = At_a[i * 3 + 0] * Rt_b[j * 3 + 0];
+  acc = fmaf(At_a[i * 3 + 1], Rt_b[j * 3 + 1], acc);
+  acc = fmaf(At_a[i * 3 + 2], Rt_b[j * 3 + 2], acc);
+  acc = fmaf(Rt_a[i * 3 + 0], At_b[j * 3 + 0], acc);
+  acc = fmaf(Rt_a[i * 3 + 1], At_b[j * 3 + 1], acc);
+  acc = fmaf(Rt_a[i * 3 + 2], At_b[j * 3 + 2], acc);
+  return -acc;
+}
+
+// One output column entry j of the pair adjoint for the frame `self`, given g3 = G[i][0..2] (a side) or
+// G[0..2][i] (b side) and the OTHER frame's folded terms:  out_At = -sum_k g3[k] Rt_o[k][j],  out_Rt = -sum_k g3[k] At_o[k][j].
+PDB_HD void pair_adjoint_entry(const float* g3, const float* At_o, const float* Rt_o, int j, float* out_At, float* out_Rt) {
+  *out_At = -(g3[0] * Rt_o[0 + j] + g3[1] * Rt_o[3 + j] + g3[2] * Rt_o[6 + j]);
+  *out_Rt = -(g3[0] * At_o[0 + j] + g3[1] * At_o[3 + j] + g3[2] * At_o[6 + j]);
+}
+
+// Per-frame: (gAt, gRt) -> (gA, gR) and the frame's contribution to d/d(ix, iy, kx, ky).
+PDB_HD void frame_unfold(const float* A, const float* R, const float* kin, const float* gAt, const float* gRt, float* gA,
+                         float* gR, float* gk) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    gA[0 + j] = kin[0] * gAt[0 + j] + kin[2] * gAt[6 + j];
+    gA[3 + j] = kin[1] * gAt[3 + j] + kin[3] * gAt[6 + j];
+    gA[6 + j] = gAt[6 + j];
+    gR[0 + j] = kin[0] * gRt[0 + j] + kin[2] * gRt[6 + j];
+    gR[3 + j] = kin[1] * gRt[3 + j] + kin[3] * gRt[6 + j];
+    gR[6 + j] = gRt[6 + j];
+  }
+  auto gKi = [&](int i, int j) {  // sum_k A[i][k] gAt[j][k] + R[i][k] gRt[j][k]
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc += A[i * 3 + k] * gAt[j * 3 + k] + R[i * 3 + k] * gRt[j * 3 + k];
+    return acc;
+  };
+  gk[0] = gKi(0, 0);
+  gk[1] = gKi(1, 1);
+  gk[2] = gKi(0, 2);
+  gk[3] = gKi(1, 2);
+}
+
 }  // namespace pdb

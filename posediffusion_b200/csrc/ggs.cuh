@@ -3,27 +3,32 @@
 // batch of independent sequences, with no host round trip.
 //
 // Per inner iteration (reference: one compute_sampson_distance forward + autograd backward + clip + SGD step):
-//   stage 0  every CTA turns the pose (kept in shared memory, identical in all CTAs of the group) into the
-//            per-frame terms and the F' matrices of the pair segments it owns;
-//   stage 1  the CTA's warps stream their slice of the packed matches (16 B per match, coalesced float4), and
-//            accumulate the error statistics and the per-pair 3x3 gradient G = sum d err / d F' in registers;
-//            warp-reduce with 16 shuffles, then shared-memory atomics per segment;
-//   stage 2a the per-pair adjoint (G -> per-frame gR, gA, intrinsics) and per-frame adjoint (-> gT, gq) are
-//            applied locally; the CTA flushes 7 floats per touched frame + 4 scalars with global atomics;
-//   barrier  one group-wide barrier (the only one per iteration; accumulators are triple-buffered);
-//   stage 2b every CTA redundantly finishes the step from the summed gradient: early-exit test, gradient
-//            mask, norm-relative clip, momentum, update of its own copy of the pose.
+//   stage 0  every CTA turns the pose (kept in shared memory, identical in all CTAs of the group) into per-frame
+//            terms: R_cv, A = hat(t) R_cv, the shared mean focal length, and the K-folded At = K^-T A, Rt = K^-T R;
+//   stage 1  each warp streams its contiguous slice of the packed matches (16 B per match, coalesced float4,
+//            kGgsUnroll rounds in flight); F' of the current pair is 9 lanes x 6 FMAs + shuffles; the error
+//            statistics and the 3x3 gradient G = sum d err / d F' accumulate in registers, then one 16-shuffle
+//            warp reduction and shared-memory adds per (warp, pair segment);
+//   stage 2a one warp per pair segment applies the pair adjoint on 18 lanes (G -> gAt, gRt of both frames);
+//   stage 2b one thread per touched frame unfolds K and applies the frame adjoint (-> gT, gq); the CTA flushes
+//            7 floats per touched frame + 4 scalars with global atomics;
+//   barrier  one group-wide barrier per iteration (the gradient accumulators are triple-buffered);
+//   stage 3  every CTA redundantly finishes the step from the summed gradient: early-exit test, gradient mask,
+//            norm-relative clip, momentum, update of its own copy of the pose.
 #pragma once
 #include "geom.cuh"
 #include "posediff_b200.h"
 
 namespace pdb {
 
-constexpr int kGgsThreads = 1024;
+constexpr int kGgsThreads = 512;
+constexpr int kGgsWarps = kGgsThreads / 32;
 constexpr int kGgsMaxSeg = 128;   // pair segments handled per chunk by one CTA
 constexpr int kGgsUnroll = 4;     // rounds (of 32 matches) in flight per warp
 constexpr int kAccTail = 4;       // {g_fx', g_fy', clamp_sum, valid error sum (eval mode)}
-constexpr int kSegAcc = 11;       // per-segment shared accumulators: G[9], clamp_sum, valid error sum
+constexpr int kAccPad = 32;        // each global accumulator sits in its own 128-byte line: 148 CTAs adding into 5 lines
+                                  // serialise on a few L2 slices; one line per value spreads them over the whole L2
+constexpr int kSegAcc = 12;       // per-segment shared accumulators: G[9], clamp_sum, valid error sum, pad
 
 struct GgsProblem {
   const float4* pts;    // [rounds*32] (u1,v1,u2,v2), padded per segment to 32-row rounds
@@ -42,6 +47,7 @@ struct GgsProblem {
   float* dbg_scalars;   // eval mode: [4]
   float* dbg_F;         // eval mode, may be null: [nseg*9]
   float* dbg_G;         // eval mode, may be null: [nseg*9], zero on entry
+  long long* dbg_clock; // may be null: [ctas][8] per-stage cycle sums (stage timing probe)
 };
 
 struct GgsParams {
@@ -51,33 +57,29 @@ struct GgsParams {
   int flags[PDB_GGS_PHASES];  // bit0 R, bit1 T, bit2 FL
   float alpha, lr, smax, momentum;
   double min_matches;
+  int resident_rounds;  // rounds of 32 matches that fit the CTA's shared-memory match cache (0 = always stream)
 };
 
-inline size_t ggs_smem_bytes(int frames) {
-  size_t f = 0;
-  f += 2 * frames * 9;            // pose, velocity
-  f += frames * (9 + 9 + 2 + 2);  // R, A, fl, inr
-  f += frames * 18;               // gR, gA accumulators
-  f += frames * 9;                // gradient scratch
-  f += 32;                        // scalars
-  f += kGgsMaxSeg * (9 + kSegAcc);  // F', segment accumulators
-  size_t bytes = f * sizeof(float);
+constexpr int kGgsFixedFloatsPerFrame = 2 * 9 + 4 * 9 + 4 + 18 + 7;  // pose, vel, R, A, Rt, At, fl, inr, gAt|gRt, summed gradient
+
+__host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
+  size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 96 + (size_t)kGgsMaxSeg * kSegAcc);
   bytes += kGgsMaxSeg * sizeof(int);         // segment valid counts
   bytes += (kGgsMaxSeg + 1) * sizeof(int4);  // segment descriptors
-  return bytes + 64;
+  return (bytes + 127) / 128 * 128;
 }
 
-__device__ __forceinline__ void atomic_add_shared(float* p, float v) { atomicAdd(p, v); }
-
+// One CTA of the group that owns one sequence.  See the file header for the stage structure.
+// `resident_rounds` > 0: the CTA's whole slice of matches (<= resident_rounds rounds) is staged in shared memory
+// once per launch and every inner iteration streams it from there (no L2/HBM traffic inside the loop).
 template <bool kEval>
 __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kWarps = kGgsThreads / 32;
   const int cpp = P.ctas_per_problem;
   const int cta = blockIdx.x % cpp;
   const int N = pr.frames, N9 = N * 9;
-  const int acc_stride = N * 7 + kAccTail;
+  const int acc_stride = (N * 7 + kAccTail) * kAccPad;
 
   // ---- shared memory carve-up ----
   int4* s_seg = reinterpret_cast<int4*>(smem_raw);
@@ -85,22 +87,25 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   float* s_vel = s_pose + N9;
   float* s_R = s_vel + N9;
   float* s_A = s_R + N9;
-  float* s_fl = s_A + N9;
+  float* s_Rt = s_A + N9;
+  float* s_At = s_Rt + N9;
+  float* s_fl = s_At + N9;
   float* s_inr = s_fl + 2 * N;
-  float* s_gR = s_inr + 2 * N;
-  float* s_gA = s_gR + N9;
-  float* s_grad = s_gA + N9;
-  float* s_misc = s_grad + N9;  // [0..3] kin, [4..5] fpx, [6..9] gk, [10] clamp_sum, [16..] tail scalars
-  float* s_F = s_misc + 32;
-  float* s_sacc = s_F + kGgsMaxSeg * 9;
+  float* s_fg = s_inr + 2 * N;    // [N][18]: gAt (0..8), gRt (9..17)
+  float* s_misc = s_fg + 2 * N9;  // [4] clamp_sum, [5] loss_sum, [8..] step scalars
+  float* s_red = s_misc + 32;     // [kGgsWarps][2] norm partials
+  float* s_gsum = s_red + 32;     // [N*7 + 8] summed gradient of this iteration (copied from L2 by warp 0)
+  float* s_sacc = s_gsum + N * 7 + 32;  // [kGgsMaxSeg][kSegAcc]
   int* s_scnt = reinterpret_cast<int*>(s_sacc + kGgsMaxSeg * kSegAcc);
+  float4* s_pts = reinterpret_cast<float4*>(smem_raw + ggs_smem_fixed_bytes(N));
   __shared__ int s_cta_cnt;
+  __shared__ int s_ctrl;  // 0 = continue, 1 = phase dropped
 
   // ---- static work partition: rounds -> CTAs -> warps ----
   const long long R = pr.rounds;
   const int r_cta0 = (int)(R * cta / cpp), r_cta1 = (int)(R * (cta + 1) / cpp);
-  const int r_w0 = r_cta0 + (int)((long long)(r_cta1 - r_cta0) * warp / kWarps);
-  const int r_w1 = r_cta0 + (int)((long long)(r_cta1 - r_cta0) * (warp + 1) / kWarps);
+  const int r_w0 = r_cta0 + (int)((long long)(r_cta1 - r_cta0) * warp / kGgsWarps);
+  const int r_w1 = r_cta0 + (int)((long long)(r_cta1 - r_cta0) * (warp + 1) / kGgsWarps);
   auto seg_of_round = [&](int r) {  // last segment whose first_round <= r
     int lo = 0, hi = pr.nseg;       // segs[nseg].x == rounds > r
     while (hi - lo > 1) {
@@ -113,103 +118,162 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   const int seg_lo = cta_has_work ? seg_of_round(r_cta0) : 0;
   const int seg_hi = cta_has_work ? seg_of_round(r_cta1 - 1) : -1;  // inclusive
   const int wseg0 = (r_w1 > r_w0) ? seg_of_round(r_w0) : 0;
+  const bool single_chunk = (seg_hi - seg_lo + 1) <= kGgsMaxSeg;
+  const bool resident = (r_cta1 - r_cta0) <= P.resident_rounds;
 
   for (int e = tid; e < N9; e += kGgsThreads) {
     s_pose[e] = pr.pose[e];
     s_vel[e] = 0.f;
   }
+  for (int e = tid; e < 2 * N9; e += kGgsThreads) s_fg[e] = 0.f;
+  for (int e = tid; e < kGgsMaxSeg * kSegAcc; e += kGgsThreads) s_sacc[e] = 0.f;
+  for (int e = tid; e < kGgsMaxSeg; e += kGgsThreads) s_scnt[e] = 0;
+  if (tid < 32) s_misc[tid] = 0.f;
+  if (tid == 0) { s_cta_cnt = 0; s_ctrl = 0; }
+  if (single_chunk && cta_has_work && tid <= seg_hi - seg_lo + 1) s_seg[tid] = __ldg(&pr.segs[seg_lo + tid]);
+  if (resident) {
+    const float4* src = pr.pts + (size_t)r_cta0 * 32;
+    const int count = (r_cta1 - r_cta0) * 32;
+    for (int e = tid; e < count; e += kGgsThreads) s_pts[e] = ld_stream_f4(src + e);
+  }
   const float scale = 0.5f * fminf(pr.height, pr.width);
   const float cx = 0.5f * pr.width, cy = 0.5f * pr.height;
   unsigned it_global = 0;
+  float kin[4] = {0.f, 0.f, 0.f, 0.f}, fpx = 1.f, fpy = 1.f;  // shared intrinsics (every warp holds a copy)
+
+  // Pose -> per-frame terms, four threads per frame: thread (n, j < 3) builds column j of R_cv, A = hat(t) R_cv and
+  // (after the focal mean is known) of the K-folded At, Rt; thread (n, 3) evaluates the clamped focal length.
+  // Two block barriers inside; every warp ends up with the shared intrinsics in registers.
+  auto frames_forward = [&]() {
+    float Rc[3] = {0.f, 0.f, 0.f}, Ac[3] = {0.f, 0.f, 0.f};
+    const int n = tid >> 2, j = tid & 3;
+    if (n < N) {
+      const float* p = s_pose + n * 9;
+      if (j < 3) {
+        const float w = p[3], x = p[4], y = p[5], z = p[6];
+        const float s2 = 2.0f / (w * w + x * x + y * y + z * z);
+        // row j of the pytorch3d rotation = column j of R_cv up to the signs D = diag(-1,-1,1) on the rows
+        float r0, r1, r2;
+        if (j == 0) { r0 = 1.f - s2 * (y * y + z * z); r1 = s2 * (x * y - z * w); r2 = s2 * (x * z + y * w); }
+        else if (j == 1) { r0 = s2 * (x * y + z * w); r1 = 1.f - s2 * (x * x + z * z); r2 = s2 * (y * z - x * w); }
+        else { r0 = s2 * (x * z - y * w); r1 = s2 * (y * z + x * w); r2 = 1.f - s2 * (x * x + y * y); }
+        Rc[0] = -r0; Rc[1] = -r1; Rc[2] = r2;
+        const float tx = -p[0], ty = -p[1], tz = p[2];
+        Ac[0] = -tz * Rc[1] + ty * Rc[2];
+        Ac[1] = tz * Rc[0] - tx * Rc[2];
+        Ac[2] = -ty * Rc[0] + tx * Rc[1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          s_R[n * 9 + i * 3 + j] = Rc[i];
+          s_A[n * 9 + i * 3 + j] = Ac[i];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float ev = expf(p[7 + k] + kLogFlBias);
+          s_fl[n * 2 + k] = fminf(fmaxf(ev, kFlMin), kFlMax);
+          s_inr[n * 2 + k] = (ev >= kFlMin && ev <= kFlMax) ? 1.f : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    {  // shared focal length = mean over frames (geometry_guided_sampling.py:142), reduced redundantly per warp
+      float fx = 0.f, fy = 0.f;
+      for (int m = lane; m < N; m += 32) {
+        fx += s_fl[m * 2];
+        fy += s_fl[m * 2 + 1];
+      }
+      fpx = warp_sum(fx) / (float)N * scale;
+      fpy = warp_sum(fy) / (float)N * scale;
+      kin[0] = 1.f / fpx;
+      kin[1] = 1.f / fpy;
+      kin[2] = -cx / fpx;
+      kin[3] = -cy / fpy;
+    }
+    if (n < N && j < 3) {
+      s_At[n * 9 + 0 + j] = kin[0] * Ac[0];
+      s_At[n * 9 + 3 + j] = kin[1] * Ac[1];
+      s_At[n * 9 + 6 + j] = kin[2] * Ac[0] + kin[3] * Ac[1] + Ac[2];
+      s_Rt[n * 9 + 0 + j] = kin[0] * Rc[0];
+      s_Rt[n * 9 + 3 + j] = kin[1] * Rc[1];
+      s_Rt[n * 9 + 6 + j] = kin[2] * Rc[0] + kin[3] * Rc[1] + Rc[2];
+    }
+    __syncthreads();
+  };
+  static_assert(4 * kMaxFrames <= kGgsThreads, "four threads per frame");
   __syncthreads();
+  frames_forward();
 
   for (int phase = 0; phase < P.n_phases; ++phase) {
     const int flags = P.flags[phase];
     const bool upd_R = flags & 1, upd_T = flags & 2, upd_FL = flags & 4;
     const int iters = P.iters[phase];
-    int done = 0, dropped = 0, last_valid = 0;
+    int done = 0, dropped = 0, last_valid = 0;          // tracked by warp 0
     float last_logged = __int_as_float(0x7fc00000);
     for (int iter = 0; iter < iters; ++iter) {
       float* acc = pr.gacc + (it_global % 3) * acc_stride;
       int* cnt = pr.gcnt + (it_global % 3);
-      // ================= stage 0a: per-frame terms =================
-      if (tid < N) {
-        frame_forward(s_pose + tid * 9, s_R + tid * 9, s_A + tid * 9, s_fl + tid * 2, s_inr + tid * 2);
-      }
-      for (int e = tid; e < 2 * N9; e += kGgsThreads) s_gR[e] = 0.f;  // gR and gA are contiguous
-      if (tid < 16) s_misc[tid] = 0.f;
-      if (tid == 0) s_cta_cnt = 0;
-      __syncthreads();
-      if (warp == 0) {  // shared focal length: mean over frames (geometry_guided_sampling.py:142)
-        float fx = 0.f, fy = 0.f;
-        for (int n = lane; n < N; n += 32) {
-          fx += s_fl[n * 2];
-          fy += s_fl[n * 2 + 1];
-        }
-        fx = warp_sum(fx) / (float)N * scale;
-        fy = warp_sum(fy) / (float)N * scale;
-        if (lane == 0) {
-          s_misc[0] = 1.f / fx;
-          s_misc[1] = 1.f / fy;
-          s_misc[2] = -cx / fx;
-          s_misc[3] = -cy / fy;
-          s_misc[4] = fx;
-          s_misc[5] = fy;
-        }
-      }
-      __syncthreads();
-      // ================= chunks of <= kGgsMaxSeg pair segments =================
+      long long ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0;
+      if (pr.dbg_clock && tid == 0) ck0 = clock64();
+      // ================= chunks of <= kGgsMaxSeg pair segments (one chunk in all practical cases) =================
       for (int cs = seg_lo; cs <= seg_hi; cs += kGgsMaxSeg) {
         const int ce = min(cs + kGgsMaxSeg, seg_hi + 1);
         const int nchunk = ce - cs;
-        // ---- stage 0b: F' per segment ----
-        if (tid <= nchunk) s_seg[tid] = __ldg(&pr.segs[cs + tid]);
-        for (int e = tid; e < nchunk * kSegAcc; e += kGgsThreads) s_sacc[e] = 0.f;
-        if (tid < nchunk) s_scnt[tid] = 0;
-        if (tid < nchunk) {
-          const int4 sd = __ldg(&pr.segs[cs + tid]);
-          float F[9];
-          pair_F(s_R + sd.z * 9, s_A + sd.z * 9, s_R + sd.w * 9, s_A + sd.w * 9, s_misc, sd.z == sd.w, F);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) s_F[tid * 9 + k] = F[k];
-          if (kEval && pr.dbg_F) {  // several CTAs may share a segment: they write identical values
-#pragma unroll
-            for (int k = 0; k < 9; ++k) pr.dbg_F[(size_t)(cs + tid) * 9 + k] = F[k];
-          }
+        if (!single_chunk) {
+          __syncthreads();
+          if (tid <= nchunk) s_seg[tid] = __ldg(&pr.segs[cs + tid]);
+          __syncthreads();
         }
-        __syncthreads();
-        // ---- stage 1: stream the matches ----
+        // ---- stage 1: stream the matches of this warp's rounds ----
         {
           int s = max(cs, wseg0);
           int r = (s < ce) ? max(r_w0, s_seg[s - cs].x) : r_w1;
           while (s < ce && r < r_w1) {
             const int4 sd = s_seg[s - cs];
             const int r_end = min(r_w1, s_seg[s - cs + 1].x);
+            // F' of this pair: 9 lanes x 6 FMAs from the K-folded frame terms, then broadcast
             float Fm[9];
+            {
+              float mine = 0.f;
+              if (lane < 9 && sd.z != sd.w)  // diagonal pair: F' = 0 exactly (reference quirk, see geom.cuh)
+                mine = pair_F_entry(s_At + sd.z * 9, s_Rt + sd.z * 9, s_At + sd.w * 9, s_Rt + sd.w * 9, lane / 3, lane % 3);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) Fm[k] = s_F[(s - cs) * 9 + k];
+              for (int k = 0; k < 9; ++k) Fm[k] = __shfl_sync(0xffffffffu, mine, k);
+              if (kEval && pr.dbg_F && lane < 9) pr.dbg_F[(size_t)s * 9 + lane] = mine;
+            }
             float g[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) g[k] = 0.f;
             int nval = 0;
             const int seg_first = sd.x, seg_count = sd.y;
-            for (; r < r_end; r += kGgsUnroll) {
-              float4 pt[kGgsUnroll];
-#pragma unroll
-              for (int u = 0; u < kGgsUnroll; ++u) {
-                if (r + u < r_end) pt[u] = ld_stream_f4(pr.pts + (size_t)(r + u) * 32 + lane);
-                else pt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (resident) {
+              const float4* base = s_pts + (size_t)(r - r_cta0) * 32 + lane;
+              const int nr = r_end - r;
+#pragma unroll 2
+              for (int q = 0; q < nr; ++q) {
+                const float4 pt = base[q * 32];
+                const bool inb = (r + q - seg_first) * 32 + lane < seg_count;
+                nval += sampson_match<kEval>(pt, Fm, inb, P.smax, g);
               }
+            } else {
+              for (; r < r_end; r += kGgsUnroll) {
+                float4 pt[kGgsUnroll];
 #pragma unroll
-              for (int u = 0; u < kGgsUnroll; ++u) {
-                const bool inb = (r + u < r_end) && ((r + u - seg_first) * 32 + lane < seg_count);
-                nval += sampson_match<kEval>(pt[u], Fm, inb, P.smax, g);
+                for (int u = 0; u < kGgsUnroll; ++u)
+                  if (r + u < r_end) pt[u] = ld_stream_f4(pr.pts + (size_t)(r + u) * 32 + lane);
+#pragma unroll
+                for (int u = 0; u < kGgsUnroll; ++u) {
+                  if (r + u < r_end) {  // warp-uniform
+                    const bool inb = (r + u - seg_first) * 32 + lane < seg_count;
+                    nval += sampson_match<kEval>(pt[u], Fm, inb, P.smax, g);
+                  }
+                }
               }
             }
-            // warp reduction: 16 shuffles for the 10 float slots, one redux for the count
+            // warp reduction: 16 shuffles for the float slots, one redux for the count
             const float tot = warp_reduce16(g, lane);
             const int slot = warp_reduce16_slot(lane);
-            if (!(lane & 1) && slot < kSegAcc) atomic_add_shared(&s_sacc[(s - cs) * kSegAcc + slot], tot);
+            if (!(lane & 1) && slot < 11) atomicAdd(&s_sacc[(s - cs) * kSegAcc + slot], tot);
             nval = __reduce_add_sync(0xffffffffu, nval);
             if (lane == 0 && nval) atomicAdd(&s_scnt[s - cs], nval);
             r = r_end;
@@ -217,122 +281,190 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
           }
         }
         __syncthreads();
-        // ---- stage 2a: per-pair adjoint into per-frame shared accumulators ----
-        if (tid < nchunk) {
-          const int4 sd = s_seg[tid];
-          float G[9];
+        // ---- stage 2a: per-pair adjoint, one warp per segment, 18 lanes x 2 outputs; leaves the slots zeroed ----
+        for (int sl = warp; sl < nchunk; sl += kGgsWarps) {
+          const int4 sd = s_seg[sl];
+          float* G = s_sacc + sl * kSegAcc;
+          float g3[3] = {0.f, 0.f, 0.f}, gs = 0.f;
+          const int side = lane >= 9, e = (lane - side * 9) % 9, i = e / 3, j = e - i * 3;
+          if (lane < 18) {
 #pragma unroll
-          for (int k = 0; k < 9; ++k) G[k] = s_sacc[tid * kSegAcc + k];
-          auto add = [](float* p, float v) { atomicAdd(p, v); };
-          pair_adjoint(s_R + sd.z * 9, s_A + sd.z * 9, s_R + sd.w * 9, s_A + sd.w * 9, s_misc, sd.z == sd.w, G,
-                       s_gR + sd.z * 9, s_gA + sd.z * 9, s_gR + sd.w * 9, s_gA + sd.w * 9, s_misc + 6, add);
-          atomicAdd(&s_misc[10], s_sacc[tid * kSegAcc + 9]);
-          if (kEval) atomicAdd(&s_misc[11], s_sacc[tid * kSegAcc + 10]);
-          atomicAdd(&s_cta_cnt, s_scnt[tid]);
-          if (kEval && pr.dbg_G) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) atomicAdd(&pr.dbg_G[(size_t)(cs + tid) * 9 + k], G[k]);
+            for (int k = 0; k < 3; ++k) g3[k] = side ? G[k * 3 + i] : G[i * 3 + k];
+            if (kEval && pr.dbg_G && lane < 9) atomicAdd(&pr.dbg_G[(size_t)(cs + sl) * 9 + lane], G[lane]);
+          } else if (lane < 20) {
+            gs = G[9 + (lane - 18)];
+          }
+          const int cnt_seg = s_scnt[sl];
+          __syncwarp();
+          if (lane < kSegAcc) G[lane] = 0.f;
+          if (lane == 0) s_scnt[sl] = 0;
+          if (lane < 18) {
+            const int self = side ? sd.w : sd.z, other = side ? sd.z : sd.w;
+            float oA, oR;
+            pair_adjoint_entry(g3, s_At + other * 9, s_Rt + other * 9, j, &oA, &oR);
+            atomicAdd(&s_fg[self * 18 + e], oA);
+            atomicAdd(&s_fg[self * 18 + 9 + e], oR);
+          } else if (lane == 18) {
+            atomicAdd(&s_misc[4], gs);
+            atomicAdd(&s_cta_cnt, cnt_seg);
+          } else if (lane == 19 && kEval) {
+            atomicAdd(&s_misc[5], gs);
           }
         }
-        __syncthreads();
       }
-      // ================= flush this CTA's contribution =================
-      if (tid < N) {
-        const float* gR = s_gR + tid * 9;
-        const float* gA = s_gA + tid * 9;
-        bool touched = false;
+      __syncthreads();
+      if (pr.dbg_clock && tid == 0) ck1 = clock64();
+      // ================= warp 0: frame adjoint + flush, barrier, step, next forward =================
+      if (warp == 0) {
+        float gk[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int n = lane; n < N; n += 32) {
+          float* gAt = s_fg + n * 18;
+          bool touched = false;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) touched |= (gR[k] != 0.f) | (gA[k] != 0.f);
-        if (touched) {
-          float gT[3], gq[4];
-          frame_adjoint(s_pose + tid * 9, s_R + tid * 9, gR, gA, gT, gq);
+          for (int k = 0; k < 18; ++k) touched |= (gAt[k] != 0.f);
+          if (touched) {
+            float gA[9], gR[9], k4[4], gT[3], gq[4];
+            frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
+            frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) atomicAdd(&acc[tid * 7 + k], gT[k]);
+            for (int k = 0; k < 3; ++k) atomicAdd(&acc[(n * 7 + k) * kAccPad], gT[k]);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) atomicAdd(&acc[tid * 7 + 3 + k], gq[k]);
+            for (int k = 0; k < 4; ++k) atomicAdd(&acc[(n * 7 + 3 + k) * kAccPad], gq[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gk[k] += k4[k];
+#pragma unroll
+            for (int k = 0; k < 18; ++k) gAt[k] = 0.f;
+          }
         }
-      } else if (tid == kGgsThreads - 32 && cta_has_work) {
-        const float fx = s_misc[4], fy = s_misc[5];
-        atomicAdd(&acc[N * 7 + 0], (-s_misc[6] + cx * s_misc[8]) / (fx * fx));
-        atomicAdd(&acc[N * 7 + 1], (-s_misc[7] + cy * s_misc[9]) / (fy * fy));
-        atomicAdd(&acc[N * 7 + 2], s_misc[10]);
-        if (kEval) atomicAdd(&acc[N * 7 + 3], s_misc[11]);
-        if (s_cta_cnt) atomicAdd(cnt, s_cta_cnt);
-      }
-      // ================= group barrier =================
-      group_barrier(pr.bar, (it_global + 1) * (unsigned)cpp);
-      // recycle the accumulator used two iterations from now (nobody reads or writes it at this point)
-      if (cta == 0) {
-        float* old = pr.gacc + ((it_global + 2) % 3) * acc_stride;
-        for (int e = tid; e < acc_stride; e += kGgsThreads) old[e] = 0.f;
-        if (tid == 0) pr.gcnt[(it_global + 2) % 3] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gk[k] = warp_sum(gk[k]);
+        if (lane == 0 && cta_has_work) {
+          atomicAdd(&acc[(N * 7 + 0) * kAccPad], (-gk[0] + cx * gk[2]) / (fpx * fpx));
+          atomicAdd(&acc[(N * 7 + 1) * kAccPad], (-gk[1] + cy * gk[3]) / (fpy * fpy));
+          atomicAdd(&acc[(N * 7 + 2) * kAccPad], s_misc[4]);
+          if (kEval) atomicAdd(&acc[(N * 7 + 3) * kAccPad], s_misc[5]);
+          if (s_cta_cnt) atomicAdd(cnt, s_cta_cnt);
+          s_misc[4] = 0.f;
+          s_misc[5] = 0.f;
+          s_cta_cnt = 0;
+        }
+        if (pr.dbg_clock && tid == 0) ck2 = clock64();
+        // ---- group barrier (warp 0 only; the other warps wait at the block barrier below) ----
+        warp_group_barrier(pr.bar, (it_global + 1) * (unsigned)cpp);
+        if (pr.dbg_clock && tid == 0) ck3 = clock64();
+        // recycle the accumulator used two iterations from now (nobody reads or writes it at this point)
+        if (cta == 0) {
+          float* old = pr.gacc + ((it_global + 2) % 3) * acc_stride;
+          for (int e = lane; e < N * 7 + kAccTail; e += 32) old[e * kAccPad] = 0.f;
+          if (lane == 0) pr.gcnt[(it_global + 2) % 3] = 0;
+        }
+        // ---- bring the summed gradient into shared memory: ONE L2 round trip, a single warp per CTA ----
+        const int nsum = N * 7 + kAccTail;
+        for (int e = lane; e < nsum; e += 32) s_gsum[e] = __ldcg(&acc[e * kAccPad]);
+        if (lane == 0) {
+          const int n_valid = __ldcg(cnt);
+          s_gsum[nsum] = __int_as_float(n_valid);
+          // len(valid) / N < min_matches  (:103-105), evaluated as n < min_matches * N in float64
+          s_ctrl = (!kEval && (P.min_matches > 0.0) && ((double)n_valid < P.min_matches * (double)N)) ? 1 : 0;
+        }
+        if (pr.dbg_clock && tid == 0) {
+          long long* c = pr.dbg_clock + (size_t)cta * 8;
+          const long long ck4 = clock64();
+          c[1] += ck1 - ck0; c[2] += ck2 - ck1; c[3] += ck3 - ck2; c[4] += ck4 - ck3; c[5] += 1;
+        }
       }
       ++it_global;
-      // ================= stage 2b: finish the step (identical in every CTA) =================
-      const int n_valid = __ldcg(cnt);
-      last_valid = n_valid;
-      last_logged = __ldcg(&acc[N * 7 + 2]) / (float)pr.m_total;
-      const bool drop = (P.min_matches > 0.0) && ((double)n_valid / (double)N < P.min_matches);
-      if (drop && !kEval) {
-        dropped = 1;
-        break;
-      }
-      for (int e = tid; e < N9; e += kGgsThreads) {
-        const int n = e / 9, c = e - n * 9;
-        float gsum;
-        if (c < 3) gsum = upd_T ? __ldcg(&acc[n * 7 + c]) : 0.f;
-        else if (c < 7) gsum = upd_R ? __ldcg(&acc[n * 7 + c]) : 0.f;
-        else gsum = upd_FL ? __ldcg(&acc[N * 7 + (c - 7)]) * (scale / (float)N) * s_fl[n * 2 + (c - 7)] * s_inr[n * 2 + (c - 7)] : 0.f;
-        s_grad[e] = gsum / (float)n_valid;
-      }
       __syncthreads();
-      if (kEval) {
-        if (cta == 0) {
-          for (int e = tid; e < N9; e += kGgsThreads) pr.dbg_grad[e] = s_grad[e];
-          if (tid == 0) {
-            pr.dbg_scalars[0] = __ldcg(&acc[N * 7 + 3]) / (float)n_valid;
-            pr.dbg_scalars[1] = (float)n_valid;
-            pr.dbg_scalars[2] = last_logged;
-            pr.dbg_scalars[3] = 0.f;
+      // ================= stage 3: finish the step, all threads (identical in every CTA) =================
+      long long ck5 = 0;
+      if (pr.dbg_clock && tid == 0) ck5 = clock64();
+      {
+        const int nsum = N * 7 + kAccTail;
+        const int n_valid = __float_as_int(s_gsum[nsum]);
+        last_valid = n_valid;
+        last_logged = s_gsum[N * 7 + 2] / (float)pr.m_total;
+        if (s_ctrl) {
+          dropped = 1;
+        } else {
+          const float inv_n = 1.0f / (float)n_valid;  // mean over the valid matches (:110)
+          const float gfx = upd_FL ? s_gsum[N * 7 + 0] * (scale / (float)N) : 0.f;
+          const float gfy = upd_FL ? s_gsum[N * 7 + 1] * (scale / (float)N) : 0.f;
+          constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
+          float gv[kPer];
+          float gn2 = 0.f, pn2 = 0.f;
+#pragma unroll
+          for (int q = 0; q < kPer; ++q) {
+            const int e = tid + q * kGgsThreads;
+            gv[q] = 0.f;
+            if (e < N9) {
+              const int n = e / 9, c = e - n * 9;
+              float gsum;
+              if (c < 3) gsum = upd_T ? s_gsum[n * 7 + c] : 0.f;
+              else if (c < 7) gsum = upd_R ? s_gsum[n * 7 + c] : 0.f;
+              else gsum = (c == 7 ? gfx : gfy) * s_fl[n * 2 + (c - 7)] * s_inr[n * 2 + (c - 7)];
+              const float g1 = gsum * inv_n;
+              gv[q] = g1;
+              gn2 = fmaf(g1, g1, gn2);
+              const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
+              pn2 = fmaf(pm, pm, pn2);
+              if (kEval && cta == 0) pr.dbg_grad[e] = g1;
+            }
+          }
+          if (kEval) {
+            if (cta == 0 && tid == 0) {
+              pr.dbg_scalars[0] = s_gsum[N * 7 + 3] / (float)n_valid;
+              pr.dbg_scalars[1] = (float)n_valid;
+              pr.dbg_scalars[2] = last_logged;
+              pr.dbg_scalars[3] = 0.f;
+            }
+          } else {
+            gn2 = warp_sum(gn2);
+            pn2 = warp_sum(pn2);
+            if (lane == 0) {
+              s_red[warp * 2] = gn2;
+              s_red[warp * 2 + 1] = pn2;
+            }
+            __syncthreads();
+            gn2 = 0.f;
+            pn2 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < kGgsWarps; ++wv) {  // fixed order: identical in every thread and CTA
+              gn2 += s_red[wv * 2];
+              pn2 += s_red[wv * 2 + 1];
+            }
+            const float max_norm = P.alpha * sqrtf(pn2) / P.lr;      // :119
+            const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
+            const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              if (e < N9) {
+                const float g1 = gv[q] * coef;
+                const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
+                s_vel[e] = v;
+                s_pose[e] = s_pose[e] - P.lr * v;
+              }
+            }
+            ++done;
+            __syncthreads();
+            frames_forward();  // stage 0 of the next iteration (two block barriers inside)
           }
         }
-        break;
       }
-      if (warp == 0) {
-        float gn2 = 0.f, pn2 = 0.f;
-        for (int e = lane; e < N9; e += 32) {
-          const float gv = s_grad[e];
-          gn2 = fmaf(gv, gv, gn2);
-          const float pm = (fabsf(gv) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
-          pn2 = fmaf(pm, pm, pn2);
-        }
-        gn2 = warp_sum(gn2);
-        pn2 = warp_sum(pn2);
-        if (lane == 0) {
-          const float max_norm = P.alpha * sqrtf(pn2) / P.lr;      // :119
-          const float coef = max_norm / (sqrtf(gn2) + 1e-6f);      // clip_grad_norm_
-          s_misc[16] = (coef > 1.0f) ? 1.0f : coef;                // clamp(max=1), NaN passes through
-        }
-      }
-      __syncthreads();
-      {
-        const float coef = s_misc[16];
-        for (int e = tid; e < N9; e += kGgsThreads) {
-          const float gv = s_grad[e] * coef;
-          const float v = (done == 0) ? gv : fmaf(P.momentum, s_vel[e], gv);  // SGD momentum buffer, reset per phase
-          s_vel[e] = v;
-          s_pose[e] = s_pose[e] - P.lr * v;
-        }
-      }
-      ++done;
-      __syncthreads();
+      if (pr.dbg_clock && tid == 0) pr.dbg_clock[(size_t)cta * 8 + 6] += clock64() - ck5;
+      if (kEval) break;
+      if (s_ctrl) break;  // uniform: phase dropped on "insufficient valid matches" (no update, :103-108)
     }
     if (kEval) break;
-    if (cta == 0 && tid == 0 && pr.stats) {
-      pr.stats->sampson[phase] = last_logged;
-      pr.stats->iters[phase] = done;
-      pr.stats->dropped[phase] = dropped;
-      pr.stats->n_valid[phase] = last_valid;
+    __syncthreads();
+    if (tid == 0) {
+      if (cta == 0 && pr.stats) {
+        pr.stats->sampson[phase] = last_logged;
+        pr.stats->iters[phase] = done;
+        pr.stats->dropped[phase] = dropped;
+        pr.stats->n_valid[phase] = last_valid;
+      }
+      s_ctrl = 0;
     }
     __syncthreads();
   }

@@ -133,7 +133,7 @@ def _segments(i12):
     return np.asarray(segs, dtype=np.int32)
 
 
-def _host_eval(pose, m, flags):
+def _host_eval(pose, m, flags, folded=False):
     lib = ctypes.CDLL(os.path.join(ROOT, "build", "libgeom_host.so"))
     N, _, H, W = m["img_shape"]
     pts = np.concatenate([m["kp1"], m["kp2"]], 1).astype(np.float32)
@@ -142,18 +142,23 @@ def _host_eval(pose, m, flags):
     pose = np.ascontiguousarray(pose, np.float32)
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     bits = (1 if flags[0] else 0) | (2 if flags[1] else 0) | (4 if flags[2] else 0)
-    lib.geom_host_eval(P(pose), N, ctypes.c_float(H), ctypes.c_float(W), P(pts), P(segs), len(segs), bits,
-                       ctypes.c_float(10.0), P(grad), P(sc), None, None)
+    if folded:
+        lib.geom_host_eval_folded(P(pose), N, ctypes.c_float(H), ctypes.c_float(W), P(pts), P(segs), len(segs), bits,
+                                  ctypes.c_float(10.0), P(grad), P(sc))
+    else:
+        lib.geom_host_eval(P(pose), N, ctypes.c_float(H), ctypes.c_float(W), P(pts), P(segs), len(segs), bits,
+                           ctypes.c_float(10.0), P(grad), P(sc), None, None)
     return grad, sc
 
 
 @pytest.mark.parametrize("tag", ["scene6", "ragged5", "uniform5", "diag4", "clamp4"])
 @pytest.mark.parametrize("flags", [(1, 1, 1), (0, 0, 1), (1, 0, 0), (0, 1, 0)])
-def test_device_geometry_on_host_matches_reference(tag, flags):
+@pytest.mark.parametrize("folded", [False, True])
+def test_device_geometry_on_host_matches_reference(tag, flags, folded):
     g = load_golden("sampson.npz")
     m = matches_from(g, tag)
     key = f"{tag}_f{''.join(map(str, flags))}"
-    grad, sc = _host_eval(g[f"{tag}_pose"], m, flags)
+    grad, sc = _host_eval(g[f"{tag}_pose"], m, flags, folded)
     ref = g[f"{key}_grad"]
     assert int(sc[1]) == int(g[f"{key}_n_valid"])
     assert np.array_equal(np.isnan(grad), np.isnan(ref))
