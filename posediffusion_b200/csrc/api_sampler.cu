@@ -141,7 +141,7 @@ int enqueue_denoiser(Context* ctx, DenoiserRun run, cudaStream_t st) {
   PDB_CUDA(ctx, cudaMemsetAsync(run.bar, 0, 256, st));
   const int TS = pick_token_tile(S);
   const int tiles = (S + TS - 1) / TS;
-  int grid = tiles * (3 * kDM / 32);  // widest stage (QKV)
+  int grid = tiles * (3 * kDM / kFPI);  // widest stage (QKV)
   if (grid > ctx->sm_count) grid = ctx->sm_count;
   switch (TS) {
     case 8: return launch_denoiser<8>(ctx, run, grid, st);

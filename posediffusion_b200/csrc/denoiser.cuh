@@ -12,6 +12,8 @@
 // are staged in shared memory and broadcast.  S = B*N tokens is tiny (20..160 per GPU): every stage is
 // latency / weight-bandwidth bound.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "posediff_b200.h"
 
@@ -26,7 +28,7 @@ constexpr int kHid = 128;      // mlp_hidden_dim     (denoiser.py:29)
 constexpr int kZ = 384;
 constexpr int kTEmb = 128;
 constexpr int kPoseEmb = 189;  // 9 * (2*10 + 1)
-constexpr int kPoseEmbPad = 192;
+constexpr int kPoseEmbPad = 256;  // 189 harmonic-pose columns zero-padded so that K/4 splits over 32 k-slices
 constexpr int kFirstIn = 702;
 constexpr int kT = PDB_NUM_TIMESTEPS;
 constexpr int kDenThreads = 256;
@@ -46,7 +48,7 @@ struct LayerWeights {
 };
 
 struct DenoiserDev {  // device pointers into the packed weight arena
-  const float4* w_first_x;  // [192/4][512]  (harmonic-pose columns 0..188 of _first.weight, zero padded)
+  const float4* w_first_x;  // [256/4][512]  (harmonic-pose columns 0..188 of _first.weight, zero padded)
   const float4* w_first_z;  // [384/4][512]  (columns 317..700)
   const float* w_first_pivot;  // [512]      (column 701)
   const float* b_first;        // [512]
@@ -156,53 +158,98 @@ __device__ __forceinline__ void load_pose_embed(float* __restrict__ Xs, const fl
 // ---------------------------------------------------------------------------------------------
 enum : int { kEpiNone = 0, kEpiRelu = 1, kEpiSilu = 2 };
 
-template <int TS, int K>
-__device__ __forceinline__ void linear_item(const float* __restrict__ Xs, float* __restrict__ red,
-                                            const float4* __restrict__ Wp, int O, int o0, const float* __restrict__ bias,
-                                            const float* __restrict__ add1, int ld1, const float* __restrict__ add2,
-                                            const float* __restrict__ add_row_scaled, const float* __restrict__ row_scale,
-                                            float* __restrict__ Y, int ldy, int row0, int valid_end, int epi) {
+// Work item of a linear stage: kFPI = 8 output features x one token tile, so that even the narrow stages
+// (512 outputs -> 64 items) spread over many SMs.  Inside the CTA the reduction dimension is cut into 32 k-slices:
+// lane = (ks = lane>>3, f = lane&7), slice = warp*4 + ks owns the k4-rows  i*32 + slice.  A warp-load of weights
+// touches 4 k4-rows x 128 contiguous bytes; the 4 k-slices of a warp read 64 contiguous bytes of the staged
+// activations (broadcast to the 8 feature lanes).
+constexpr int kFPI = 8;
+constexpr int kSlices = kDenWarps * 4;
+
+template <int K>
+struct LinW {
+  static constexpr int K4 = K / 4;
+  static constexpr int PER = K4 / kSlices;
+  static_assert(K4 % kSlices == 0 && PER >= 1 && PER <= 16, "K layout");
+  float4 w[PER];
+};
+
+// Issue the weight loads of one work item.  Weights never depend on activations, so this is called BEFORE the group
+// barrier that precedes the stage: the L2 latency of the weight stream hides behind the barrier.
+template <int K>
+__device__ __forceinline__ void linear_prefetch(LinW<K>& W, const float4* __restrict__ Wp, int O, int o0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int K4 = K / 4;
-  constexpr int PERW = K4 / kDenWarps;           // k4 rows per warp
-  constexpr int BATCH = PERW < 16 ? PERW : 16;   // weight loads in flight
-  static_assert(K4 % kDenWarps == 0 && PERW % BATCH == 0, "K layout");
+  const int slice = warp * 4 + (lane >> 3);
+  const float4* wp = Wp + (size_t)slice * O + o0 + (lane & 7);
+#pragma unroll
+  for (int i = 0; i < LinW<K>::PER; ++i) W.w[i] = __ldg(wp + (size_t)i * kSlices * O);
+}
+
+template <int TS, int K>
+__device__ __forceinline__ void linear_item(const LinW<K>& W, const float* __restrict__ Xs, float* __restrict__ red, int o0,
+                                            const float* __restrict__ bias, const float* __restrict__ add1, int ld1,
+                                            const float* __restrict__ add2, const float* __restrict__ add_row_scaled,
+                                            const float* __restrict__ row_scale, float* __restrict__ Y, int ldy, int row0,
+                                            int valid_end, int epi) {
+  static_assert(TS % 8 == 0, "token tile");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int PER = LinW<K>::PER;
+  const int ks = lane >> 3, f = lane & 7;
+  // epilogue operands of this thread's output (token s_out, feature f_out) are requested before the FMA loop
+  const int s_out = threadIdx.x >> 3, f_out = threadIdx.x & 7;
+  const bool has_out = s_out < TS && (row0 + s_out) < valid_end;
+  float epi_add = 0.f;
+  if (has_out) {
+    const int row = row0 + s_out, o = o0 + f_out;
+    if (bias) epi_add += __ldg(bias + o);
+    if (add1) epi_add += __ldcg(add1 + (size_t)row * ld1 + o);
+    if (add2) epi_add += __ldg(add2 + o);
+    if (add_row_scaled) epi_add += __ldg(add_row_scaled + o) * row_scale[s_out];
+  }
   float acc[TS];
 #pragma unroll
   for (int s = 0; s < TS; ++s) acc[s] = 0.f;
-  const float4* wp = Wp + (size_t)(warp * PERW) * O + o0 + lane;
-  const float* xs = Xs + warp * PERW * 4;
-#pragma unroll 1
-  for (int b = 0; b < PERW; b += BATCH) {
-    float4 w[BATCH];
+  const float* xs = Xs + (warp * 4 + ks) * 4;
 #pragma unroll
-    for (int i = 0; i < BATCH; ++i) w[i] = __ldg(wp + (size_t)(b + i) * O);
+  for (int i = 0; i < PER; ++i) {
 #pragma unroll
-    for (int i = 0; i < BATCH; ++i) {
+    for (int s = 0; s < TS; ++s) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + s * K + i * kSlices * 4);
+      acc[s] = fmaf(W.w[i].x, xv.x, fmaf(W.w[i].y, xv.y, fmaf(W.w[i].z, xv.z, fmaf(W.w[i].w, xv.w, acc[s]))));
+    }
+  }
+  // reduce over the 4 k-slices of the warp: after two exchange steps lane (ks, f) owns tokens ks*TS/4 .. +TS/4-1
+  constexpr int Q = TS / 4;
+  {
+    const bool hi = ks & 2;
 #pragma unroll
-      for (int s = 0; s < TS; ++s) {
-        const float4 xv = *reinterpret_cast<const float4*>(xs + s * K + (b + i) * 4);
-        acc[s] = fmaf(w[i].x, xv.x, fmaf(w[i].y, xv.y, fmaf(w[i].z, xv.z, fmaf(w[i].w, xv.w, acc[s]))));
-      }
+    for (int s = 0; s < TS / 2; ++s) {
+      const float send = hi ? acc[s] : acc[s + TS / 2];
+      const float keep = hi ? acc[s + TS / 2] : acc[s];
+      acc[s] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = ks & 1;
+#pragma unroll
+    for (int s = 0; s < Q; ++s) {
+      const float send = hi ? acc[s] : acc[s + Q];
+      const float keep = hi ? acc[s + Q] : acc[s];
+      acc[s] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
   }
 #pragma unroll
-  for (int s = 0; s < TS; ++s) red[(warp * TS + s) * 32 + lane] = acc[s];
+  for (int s = 0; s < Q; ++s) red[(warp * TS + ks * Q + s) * kFPI + f] = acc[s];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < TS * 32; idx += kDenThreads) {
-    const int s = idx >> 5, f = idx & 31;
-    const int row = row0 + s, o = o0 + f;
-    if (row < valid_end) {
-      float v = 0.f;
+  if (s_out < TS) {
+    float v = 0.f;
 #pragma unroll
-      for (int wv = 0; wv < kDenWarps; ++wv) v += red[(wv * TS + s) * 32 + f];
-      if (bias) v += __ldg(bias + o);
-      if (add1) v += __ldcg(add1 + (size_t)row * ld1 + o);
-      if (add2) v += __ldg(add2 + o);
-      if (add_row_scaled) v += __ldg(add_row_scaled + o) * row_scale[s];
+    for (int wv = 0; wv < kDenWarps; ++wv) v += red[(wv * TS + s_out) * kFPI + f_out];
+    if (has_out) {
+      v += epi_add;
       if (epi == kEpiRelu) v = fmaxf(v, 0.f);
       else if (epi == kEpiSilu) v = v / (1.0f + expf(-v));
-      Y[(size_t)row * ldy + o] = v;
+      Y[(size_t)(row0 + s_out) * ldy + o0 + f_out] = v;
     }
   }
   __syncthreads();
@@ -306,7 +353,7 @@ __device__ __forceinline__ void tail_token(const DenoiserDev& W, const DenoiserR
   if (lane < kTargetDim) {
     const float* sc = W.sched + t * 8;
     const size_t e = (size_t)s * kTargetDim + lane;
-    const float xt = R.x[e];
+    const float xt = __ldcg(R.x + e);
     const float x0 = sc[0] * xt - sc[1] * mine;             // predict_start_from_noise (:190-194)
     const float mu = sc[2] * x0 + sc[3] * xt;               // q_posterior mean (:201-205)
     float out = mu;
@@ -330,114 +377,99 @@ __global__ void __launch_bounds__(kDenThreads, 1)
 denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R) {
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;  // [TS][K<=1024] or attention scratch
+  __shared__ float pivot[32];
   const int S = R.tokens;
   const int tiles = (S + TS - 1) / TS;
   const int G = gridDim.x;
   unsigned bar_count = 0;
+  // Group barrier: release by one thread after the block barrier (cumulative over the CTA's writes), acquire polls.
   auto barrier = [&]() {
     ++bar_count;
-    group_barrier(R.bar, bar_count * (unsigned)G);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      red_release_add_u32(R.bar, 1u);
+      while (ld_acquire_u32(R.bar) < bar_count * (unsigned)G) {
+      }
+    }
+    __syncthreads();
   };
+  // One linear stage: Y = epi(X' W^T + ...), work items = (token tile, 32-feature group).  The weights of this CTA's
+  // first item are requested BEFORE the barrier that closes the previous stage (`need_barrier`), the activations after.
+  auto linear_stage = [&](auto ktag, const float4* Wp, int O, auto&& load_x, const float* bias, const float* add1, int ld1,
+                          const float* add2, const float* add_rs, const float* rs, float* Y, int ldy, int epi,
+                          bool need_barrier) {
+    constexpr int K = decltype(ktag)::value;
+    const int groups = O / kFPI;
+    const int n_items = tiles * groups;
+    LinW<K> wreg;
+    int item = blockIdx.x;
+    if (item < n_items) linear_prefetch<K>(wreg, Wp, O, (item % groups) * kFPI);
+    if (need_barrier) barrier();
+    float* red = Xs + TS * K;
+    for (; item < n_items; item += G) {
+      const int tt = item / groups, fg = item - tt * groups;
+      if (item != (int)blockIdx.x) linear_prefetch<K>(wreg, Wp, O, fg * kFPI);
+      load_x(tt);
+      __syncthreads();
+      linear_item<TS, K>(wreg, Xs, red, fg * kFPI, bias, add1, ld1, add2, add_rs, rs, Y, ldy, tt * TS, S, epi);
+    }
+  };
+  bool pending = false;  // a stage has written global activations that the next stage must wait for
   // ---- loop-invariant: zproj = z @ Wz^T + b_first + pivot * w_pivot   (denoiser.py:62-70) ----
   if (R.compute_zproj) {
-    float* red = Xs + TS * kZ;
-    for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
-      const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
-      load_rows<kZ>(Xs, R.z, tt * TS, TS, S, nullptr, nullptr);
-      __shared__ float pivot[32];
-      if (threadIdx.x < TS) pivot[threadIdx.x] = ((tt * TS + threadIdx.x) % R.frames == 0) ? 1.f : 0.f;
-      __syncthreads();
-      linear_item<TS, kZ>(Xs, red, W.w_first_z, kDM, fg * 32, W.b_first, nullptr, 0, nullptr, W.w_first_pivot, pivot,
-                          R.zproj, kDM, tt * TS, S, kEpiNone);
-    }
-    barrier();
+    linear_stage(std::integral_constant<int, kZ>{}, W.w_first_z, kDM,
+                 [&](int tt) {
+                   load_rows<kZ>(Xs, R.z, tt * TS, TS, S, nullptr, nullptr);
+                   if (threadIdx.x < TS) pivot[threadIdx.x] = ((tt * TS + threadIdx.x) % R.frames == 0) ? 1.f : 0.f;
+                 },
+                 W.b_first, nullptr, 0, nullptr, W.w_first_pivot, pivot, R.zproj, kDM, kEpiNone, false);
+    pending = true;
   }
   for (int t = R.t_hi; t >= R.t_lo; --t) {
     // ---- embed + first ----
-    {
-      float* red = Xs + TS * kPoseEmbPad;
-      for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
-        const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
-        load_pose_embed(Xs, R.x, tt * TS, TS, S);
-        __syncthreads();
-        linear_item<TS, kPoseEmbPad>(Xs, red, W.w_first_x, kDM, fg * 32, nullptr, R.zproj, kDM, W.tproj + t * kDM, nullptr,
-                                     nullptr, R.h, kDM, tt * TS, S, kEpiNone);
-      }
-      barrier();
-    }
+    linear_stage(std::integral_constant<int, kPoseEmbPad>{}, W.w_first_x, kDM,
+                 [&](int tt) { load_pose_embed(Xs, R.x, tt * TS, TS, S); }, nullptr, R.zproj, kDM, W.tproj + t * kDM, nullptr,
+                 nullptr, R.h, kDM, kEpiNone, pending);
+    pending = true;
     for (int l = 0; l < kLayers; ++l) {
       const LayerWeights& L = W.layer[l];
-      {  // LN1 + QKV projection
-        float* red = Xs + TS * kDM;
-        for (int item = blockIdx.x; item < tiles * (3 * kDM / 32); item += G) {
-          const int tt = item / (3 * kDM / 32), fg = item - tt * (3 * kDM / 32);
-          load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln1_g, L.ln1_b);
-          __syncthreads();
-          linear_item<TS, kDM>(Xs, red, L.w_qkv, 3 * kDM, fg * 32, L.b_qkv, nullptr, 0, nullptr, nullptr, nullptr, R.qkv,
-                               3 * kDM, tt * TS, S, kEpiNone);
-        }
-        barrier();
-      }
-      {  // attention per (sequence, head)
-        for (int item = blockIdx.x; item < R.batch * kHeads; item += G)
-          attention_item(Xs, R.qkv, R.att, item / kHeads, item % kHeads, R.frames);
-        barrier();
-      }
-      {  // out-proj + residual (in place on h: each element is read and written by the same thread)
-        float* red = Xs + TS * kDM;
-        for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
-          const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
-          load_rows<kDM>(Xs, R.att, tt * TS, TS, S, nullptr, nullptr);
-          __syncthreads();
-          linear_item<TS, kDM>(Xs, red, L.w_out, kDM, fg * 32, L.b_out, R.h, kDM, nullptr, nullptr, nullptr, R.h, kDM,
-                               tt * TS, S, kEpiNone);
-        }
-        barrier();
-      }
-      {  // LN2 + FF1 + ReLU
-        float* red = Xs + TS * kDM;
-        for (int item = blockIdx.x; item < tiles * (kFF / 32); item += G) {
-          const int tt = item / (kFF / 32), fg = item - tt * (kFF / 32);
-          load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln2_g, L.ln2_b);
-          __syncthreads();
-          linear_item<TS, kDM>(Xs, red, L.w_ff1, kFF, fg * 32, L.b_ff1, nullptr, 0, nullptr, nullptr, nullptr, R.ff, kFF,
-                               tt * TS, S, kEpiRelu);
-        }
-        barrier();
-      }
-      {  // FF2 + residual
-        float* red = Xs + TS * kFF;
-        for (int item = blockIdx.x; item < tiles * (kDM / 32); item += G) {
-          const int tt = item / (kDM / 32), fg = item - tt * (kDM / 32);
-          load_rows<kFF>(Xs, R.ff, tt * TS, TS, S, nullptr, nullptr);
-          __syncthreads();
-          linear_item<TS, kFF>(Xs, red, L.w_ff2, kDM, fg * 32, L.b_ff2, R.h, kDM, nullptr, nullptr, nullptr, R.h, kDM,
-                               tt * TS, S, kEpiNone);
-        }
-        barrier();
-      }
-    }
-    {  // last0: Linear(512 -> 128)
-      float* red = Xs + TS * kDM;
-      for (int item = blockIdx.x; item < tiles * (kHid / 32); item += G) {
-        const int tt = item / (kHid / 32), fg = item - tt * (kHid / 32);
-        load_rows<kDM>(Xs, R.h, tt * TS, TS, S, nullptr, nullptr);
-        __syncthreads();
-        linear_item<TS, kDM>(Xs, red, W.w_last0, kHid, fg * 32, W.b_last0, nullptr, 0, nullptr, nullptr, nullptr, R.u, kHid,
-                             tt * TS, S, kEpiNone);
-      }
+      // LN1 + QKV projection
+      linear_stage(std::integral_constant<int, kDM>{}, L.w_qkv, 3 * kDM,
+                   [&](int tt) { load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln1_g, L.ln1_b); }, L.b_qkv, nullptr, 0, nullptr,
+                   nullptr, nullptr, R.qkv, 3 * kDM, kEpiNone, true);
+      // attention per (sequence, head)
       barrier();
+      for (int item = blockIdx.x; item < R.batch * kHeads; item += G)
+        attention_item(Xs, R.qkv, R.att, item / kHeads, item % kHeads, R.frames);
+      // out-proj + residual (in place on h: each element is read and written by the same thread)
+      linear_stage(std::integral_constant<int, kDM>{}, L.w_out, kDM,
+                   [&](int tt) { load_rows<kDM>(Xs, R.att, tt * TS, TS, S, nullptr, nullptr); }, L.b_out, R.h, kDM, nullptr,
+                   nullptr, nullptr, R.h, kDM, kEpiNone, true);
+      // LN2 + FF1 + ReLU
+      linear_stage(std::integral_constant<int, kDM>{}, L.w_ff1, kFF,
+                   [&](int tt) { load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln2_g, L.ln2_b); }, L.b_ff1, nullptr, 0, nullptr,
+                   nullptr, nullptr, R.ff, kFF, kEpiRelu, true);
+      // FF2 + residual
+      linear_stage(std::integral_constant<int, kFF>{}, L.w_ff2, kDM,
+                   [&](int tt) { load_rows<kFF>(Xs, R.ff, tt * TS, TS, S, nullptr, nullptr); }, L.b_ff2, R.h, kDM, nullptr,
+                   nullptr, nullptr, R.h, kDM, kEpiNone, true);
     }
-    {  // tail: one warp per token
+    // last0: Linear(512 -> 128)
+    linear_stage(std::integral_constant<int, kDM>{}, W.w_last0, kHid,
+                 [&](int tt) { load_rows<kDM>(Xs, R.h, tt * TS, TS, S, nullptr, nullptr); }, W.b_last0, nullptr, 0, nullptr,
+                 nullptr, nullptr, R.u, kHid, kEpiNone, true);
+    // tail: one warp per token
+    barrier();
+    {
       const int warp_global = blockIdx.x * kDenWarps + (threadIdx.x >> 5);
       for (int s = warp_global; s < S; s += G * kDenWarps) tail_token(W, R, s, t, t == R.t_lo);
-      barrier();
     }
+    pending = true;
   }
 }
 
 inline size_t denoiser_smem_bytes(int TS, int frames) {
-  size_t lin = (size_t)TS * kFF + (size_t)kDenWarps * TS * 32;                        // X tile + reduction
+  size_t lin = (size_t)TS * kFF + (size_t)kDenWarps * TS * kFPI;                      // X tile + reduction
   size_t att = (size_t)frames * (kHD + 1) + 4 + (size_t)frames * kHD + 2 * kDenWarps * kHD;  // K, V, Q, P
   return sizeof(float) * (lin > att ? lin : att) + 256;
 }
