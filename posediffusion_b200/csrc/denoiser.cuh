@@ -86,48 +86,60 @@ inline size_t denoiser_ws_floats(int tokens) {
 // ---------------------------------------------------------------------------------------------
 // token-tile loaders (global -> shared), one warp per row
 // ---------------------------------------------------------------------------------------------
-// plain copy or LayerNorm of a [rows, K] slab; rows >= valid are zero-filled
-template <int K>
-__device__ __forceinline__ void load_rows(float* __restrict__ Xs, const float* __restrict__ src, int row0, int rows,
-                                          int valid_end, const float* __restrict__ ln_g, const float* __restrict__ ln_b) {
+// plain copy or LayerNorm of a [rows, K] slab; rows >= valid are zero-filled.  All global loads of the tile are
+// issued before any is consumed (ONE L2 round trip per stage); the LayerNorm then runs out of shared memory.
+template <int K, int TS>
+__device__ __forceinline__ void load_rows(float* __restrict__ Xs, const float* __restrict__ src, int row0, int valid_end,
+                                          const float* __restrict__ ln_g, const float* __restrict__ ln_b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int PER = K / 128;  // float4 per lane
-  for (int r = warp; r < rows; r += kDenWarps) {
-    const int s = row0 + r;
-    float4 v[PER];
-    if (s < valid_end) {
-      const float4* p = reinterpret_cast<const float4*>(src + (size_t)s * K);
+  constexpr int K4 = K / 4;
+  constexpr int TOTAL = TS * K4;                    // float4 elements of the tile
+  constexpr int PER = (TOTAL + kDenThreads - 1) / kDenThreads;
+  float4 v[PER];
 #pragma unroll
-      for (int i = 0; i < PER; ++i) v[i] = __ldcg(p + lane + 32 * i);
-      if (ln_g) {
-        float sum = 0.f;
+  for (int i = 0; i < PER; ++i) {
+    const int idx = threadIdx.x + i * kDenThreads;
+    const int r = idx / K4, c = idx - r * K4;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < TOTAL && row0 + r < valid_end) v[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * K) + c);
+  }
 #pragma unroll
-        for (int i = 0; i < PER; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
-        const float mean = warp_sum(sum) * (1.0f / K);
-        float sq = 0.f;
+  for (int i = 0; i < PER; ++i) {
+    const int idx = threadIdx.x + i * kDenThreads;
+    if (idx < TOTAL) reinterpret_cast<float4*>(Xs)[idx] = v[i];
+  }
+  if (ln_g) {
+    __syncthreads();
+    constexpr int PL = K / 128;  // float4 per lane per row
+    for (int r = warp; r < TS; r += kDenWarps) {
+      if (row0 + r >= valid_end) continue;
+      float4* row = reinterpret_cast<float4*>(Xs + (size_t)r * K);
+      float4 x[PL];
+      float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-          v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-          sq += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-        }
-        const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / K) + kLnEps);
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g) + lane + 32 * i);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(ln_b) + lane + 32 * i);
-          v[i].x = v[i].x * rstd * g.x + b.x;
-          v[i].y = v[i].y * rstd * g.y + b.y;
-          v[i].z = v[i].z * rstd * g.z + b.z;
-          v[i].w = v[i].w * rstd * g.w + b.w;
-        }
+      for (int i = 0; i < PL; ++i) {
+        x[i] = row[lane + 32 * i];
+        sum += x[i].x + x[i].y + x[i].z + x[i].w;
       }
-    } else {
+      const float mean = warp_sum(sum) * (1.0f / K);
+      float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < PER; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < PL; ++i) {
+        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+        sq += x[i].x * x[i].x + x[i].y * x[i].y + x[i].z * x[i].z + x[i].w * x[i].w;
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / K) + kLnEps);
+#pragma unroll
+      for (int i = 0; i < PL; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g) + lane + 32 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ln_b) + lane + 32 * i);
+        x[i].x = x[i].x * rstd * g.x + b.x;
+        x[i].y = x[i].y * rstd * g.y + b.y;
+        x[i].z = x[i].z * rstd * g.z + b.z;
+        x[i].w = x[i].w * rstd * g.w + b.w;
+        row[lane + 32 * i] = x[i];
+      }
     }
-    float4* d = reinterpret_cast<float4*>(Xs + (size_t)r * K);
-#pragma unroll
-    for (int i = 0; i < PER; ++i) d[lane + 32 * i] = v[i];
   }
 }
 
@@ -259,41 +271,44 @@ __device__ __forceinline__ void linear_item(const LinW<K>& W, const float* __res
 // Self-attention for one (sequence, head): N <= 128 keys, head dim 128, fp32.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void attention_item(float* __restrict__ smem, const float* __restrict__ qkv,
-                                               float* __restrict__ att, int seq, int head, int N) {
+                                               float* __restrict__ att, int seq, int head, int chunk, int N) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int KP = kHD + 1;  // padded key rows: lane = key index reads are conflict free
-  float* Ks = smem;                 // [N][129]
-  float* Vs = Ks + ((N * KP + 3) & ~3);  // [N][128], 16-byte aligned
-  float* Qs = Vs + N * kHD;         // [warps][128]
-  float* Ps = Qs + kDenWarps * kHD; // [warps][128]
+  constexpr int KP = kHD + 4;  // padded key rows (float4 aligned): lane = key index reads hit distinct banks
+  float* Ks = smem;                        // [N][132]
+  float* Vs = Ks + N * KP;                 // [N][128]
+  float* Qs = Vs + N * kHD;                // [warps][128]
+  float* Ps = Qs + kDenWarps * kHD;        // [warps][128]
   const float* base = qkv + (size_t)seq * N * (3 * kDM) + head * kHD;
-  for (int i = threadIdx.x; i < N * (kHD / 4); i += kDenThreads) {
-    const int j = i / (kHD / 4), d4 = i - j * (kHD / 4);
+  const int i = chunk * kDenWarps + warp;  // this warp's query row
+  float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < N) qv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)i * 3 * kDM) + lane);
+  for (int e = threadIdx.x; e < N * (kHD / 4); e += kDenThreads) {
+    const int j = e / (kHD / 4), d4 = e - j * (kHD / 4);
     const float4 kv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + kDM) + d4);
     const float4 vv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + 2 * kDM) + d4);
-    Ks[j * KP + d4 * 4 + 0] = kv.x; Ks[j * KP + d4 * 4 + 1] = kv.y; Ks[j * KP + d4 * 4 + 2] = kv.z; Ks[j * KP + d4 * 4 + 3] = kv.w;
+    *reinterpret_cast<float4*>(Ks + j * KP + d4 * 4) = kv;
     *reinterpret_cast<float4*>(Vs + j * kHD + d4 * 4) = vv;
   }
-  __syncthreads();
   const float scaling = 0.08838834764831845f;  // 1/sqrt(128): q is scaled before QK^T (torch MHA)
-  for (int i = warp; i < N; i += kDenWarps) {
-    const float4 qv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)i * 3 * kDM) + lane);
-    *reinterpret_cast<float4*>(Qs + warp * kHD + lane * 4) = make_float4(qv.x * scaling, qv.y * scaling, qv.z * scaling, qv.w * scaling);
-    __syncwarp();
+  *reinterpret_cast<float4*>(Qs + warp * kHD + lane * 4) = make_float4(qv.x * scaling, qv.y * scaling, qv.z * scaling, qv.w * scaling);
+  __syncthreads();
+  if (i < N) {
     float sc[4];  // up to 128 keys: 4 passes of 32
     float mx = -INFINITY;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int j = p * 32 + lane;
       float dot = -INFINITY;
-      if (p * 32 < N) {
-        if (j < N) {
-          dot = 0.f;
-          const float* kr = Ks + j * KP;
-          const float* qr = Qs + warp * kHD;
-#pragma unroll 16
-          for (int d = 0; d < kHD; ++d) dot = fmaf(qr[d], kr[d], dot);
+      if (p * 32 < N && j < N) {
+        const float4* kr = reinterpret_cast<const float4*>(Ks + j * KP);
+        const float4* qr = reinterpret_cast<const float4*>(Qs + warp * kHD);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < kHD / 4; ++d) {
+          const float4 a = qr[d], b = kr[d];
+          d0 = fmaf(a.x, b.x, d0); d1 = fmaf(a.y, b.y, d1); d2 = fmaf(a.z, b.z, d2); d3 = fmaf(a.w, b.w, d3);
         }
+        dot = (d0 + d1) + (d2 + d3);
       }
       sc[p] = dot;
       mx = fmaxf(mx, dot);
@@ -323,7 +338,6 @@ __device__ __forceinline__ void attention_item(float* __restrict__ smem, const f
       o4.x = fmaf(pj, vv.x, o4.x); o4.y = fmaf(pj, vv.y, o4.y); o4.z = fmaf(pj, vv.z, o4.z); o4.w = fmaf(pj, vv.w, o4.w);
     }
     *reinterpret_cast<float4*>(att + ((size_t)seq * N + i) * kDM + head * kHD + lane * 4) = o4;
-    __syncwarp();
   }
   __syncthreads();
 }
@@ -419,7 +433,7 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
   if (R.compute_zproj) {
     linear_stage(std::integral_constant<int, kZ>{}, W.w_first_z, kDM,
                  [&](int tt) {
-                   load_rows<kZ>(Xs, R.z, tt * TS, TS, S, nullptr, nullptr);
+                   load_rows<kZ, TS>(Xs, R.z, tt * TS, S, nullptr, nullptr);
                    if (threadIdx.x < TS) pivot[threadIdx.x] = ((tt * TS + threadIdx.x) % R.frames == 0) ? 1.f : 0.f;
                  },
                  W.b_first, nullptr, 0, nullptr, W.w_first_pivot, pivot, R.zproj, kDM, kEpiNone, false);
@@ -435,28 +449,31 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
       const LayerWeights& L = W.layer[l];
       // LN1 + QKV projection
       linear_stage(std::integral_constant<int, kDM>{}, L.w_qkv, 3 * kDM,
-                   [&](int tt) { load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln1_g, L.ln1_b); }, L.b_qkv, nullptr, 0, nullptr,
+                   [&](int tt) { load_rows<kDM, TS>(Xs, R.h, tt * TS, S, L.ln1_g, L.ln1_b); }, L.b_qkv, nullptr, 0, nullptr,
                    nullptr, nullptr, R.qkv, 3 * kDM, kEpiNone, true);
       // attention per (sequence, head)
       barrier();
-      for (int item = blockIdx.x; item < R.batch * kHeads; item += G)
-        attention_item(Xs, R.qkv, R.att, item / kHeads, item % kHeads, R.frames);
+      {
+        const int chunks = (R.frames + kDenWarps - 1) / kDenWarps;
+        for (int item = blockIdx.x; item < R.batch * kHeads * chunks; item += G)
+          attention_item(Xs, R.qkv, R.att, item / (kHeads * chunks), (item / chunks) % kHeads, item % chunks, R.frames);
+      }
       // out-proj + residual (in place on h: each element is read and written by the same thread)
       linear_stage(std::integral_constant<int, kDM>{}, L.w_out, kDM,
-                   [&](int tt) { load_rows<kDM>(Xs, R.att, tt * TS, TS, S, nullptr, nullptr); }, L.b_out, R.h, kDM, nullptr,
+                   [&](int tt) { load_rows<kDM, TS>(Xs, R.att, tt * TS, S, nullptr, nullptr); }, L.b_out, R.h, kDM, nullptr,
                    nullptr, nullptr, R.h, kDM, kEpiNone, true);
       // LN2 + FF1 + ReLU
       linear_stage(std::integral_constant<int, kDM>{}, L.w_ff1, kFF,
-                   [&](int tt) { load_rows<kDM>(Xs, R.h, tt * TS, TS, S, L.ln2_g, L.ln2_b); }, L.b_ff1, nullptr, 0, nullptr,
+                   [&](int tt) { load_rows<kDM, TS>(Xs, R.h, tt * TS, S, L.ln2_g, L.ln2_b); }, L.b_ff1, nullptr, 0, nullptr,
                    nullptr, nullptr, R.ff, kFF, kEpiRelu, true);
       // FF2 + residual
       linear_stage(std::integral_constant<int, kFF>{}, L.w_ff2, kDM,
-                   [&](int tt) { load_rows<kFF>(Xs, R.ff, tt * TS, TS, S, nullptr, nullptr); }, L.b_ff2, R.h, kDM, nullptr,
+                   [&](int tt) { load_rows<kFF, TS>(Xs, R.ff, tt * TS, S, nullptr, nullptr); }, L.b_ff2, R.h, kDM, nullptr,
                    nullptr, nullptr, R.h, kDM, kEpiNone, true);
     }
     // last0: Linear(512 -> 128)
     linear_stage(std::integral_constant<int, kDM>{}, W.w_last0, kHid,
-                 [&](int tt) { load_rows<kDM>(Xs, R.h, tt * TS, TS, S, nullptr, nullptr); }, W.b_last0, nullptr, 0, nullptr,
+                 [&](int tt) { load_rows<kDM, TS>(Xs, R.h, tt * TS, S, nullptr, nullptr); }, W.b_last0, nullptr, 0, nullptr,
                  nullptr, nullptr, R.u, kHid, kEpiNone, true);
     // tail: one warp per token
     barrier();
@@ -470,7 +487,7 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
 
 inline size_t denoiser_smem_bytes(int TS, int frames) {
   size_t lin = (size_t)TS * kFF + (size_t)kDenWarps * TS * kFPI;                      // X tile + reduction
-  size_t att = (size_t)frames * (kHD + 1) + 4 + (size_t)frames * kHD + 2 * kDenWarps * kHD;  // K, V, Q, P
+  size_t att = (size_t)frames * (kHD + 4) + (size_t)frames * kHD + 2 * kDenWarps * kHD;  // K, V, Q, P
   return sizeof(float) * (lin > att ? lin : att) + 256;
 }
 
