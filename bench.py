@@ -153,7 +153,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = os.cpu_count() or 1
+        # PyTorch-CPU scales poorly past ~32 threads on these ~1e6-element ops (128-thread runs are slower): use the
+        # host threads it can use, capped at 32, and say so in `cores`
+        threads = min(os.cpu_count() or 1, int(os.environ.get("PDB_REF_THREADS", "32")))
         res = cpu_reference_run(frames, per_pair, args.seed, threads, args.cpu_budget * max(1, args.steps))
         line = {
             "impl": "reference", "metric": "diffusion steps/sec (20-frame seq, GGS on)", "value": res["steps_per_s"],

@@ -1,6 +1,6 @@
 """Stage timing probe of the GGS kernel (debug helper, run on the GPU box)."""
 import sys, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import posediffusion_b200 as pdb
 from posediffusion_b200 import synthetic as syn, _native
 frames, per_pair = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (20, 2048)
