@@ -1,8 +1,10 @@
 // C-ABI entry points: context, correspondences, Sampson evaluation, geometry-guided sampling.
 // (include/posediff_b200.h documents which reference call site each one replaces.)
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "context.cuh"
 #include "ggs.cuh"
@@ -186,14 +188,52 @@ int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const
   if (rounds > 0x7fffffffLL / 32) return ctx->fail(PDB_ERR_LIMIT, "too many matches");
   const int nseg = (int)segs.size();
   segs.push_back(make_int4((int)rounds, 0, 0, 0));
-  // pass 2: fp32 quads, padded to 32-row rounds per segment
-  std::vector<float4> pts((size_t)rounds * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+  // pass 2: fp32 quads, padded to 32-row rounds per segment, written straight into pinned staging memory
+  const size_t pts_bytes = sizeof(float4) * ((size_t)rounds * 32 ? (size_t)rounds * 32 : 1);
+  const size_t segs_bytes = sizeof(int4) * segs.size();
+  const size_t stage_need = pts_bytes + segs_bytes;
+  if (ctx->pin_bytes < stage_need) {
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr;
+    ctx->pin_bytes = 0;
+    PDB_CUDA(ctx, cudaHostAlloc(&ctx->pin, stage_need + stage_need / 4, cudaHostAllocDefault));
+    ctx->pin_bytes = stage_need + stage_need / 4;
+  }
+  float4* hpts = static_cast<float4*>(ctx->pin);
+  int4* hsegs = reinterpret_cast<int4*>(static_cast<char*>(ctx->pin) + pts_bytes);
+  memcpy(hsegs, segs.data(), segs_bytes);
   {
-    int64_t src = 0;
-    for (int s = 0; s < nseg; ++s) {
-      float4* dst = pts.data() + (size_t)segs[s].x * 32;
-      for (int k = 0; k < segs[s].y; ++k, ++src)
-        dst[k] = make_float4((float)kp1[2 * src], (float)kp1[2 * src + 1], (float)kp2[2 * src], (float)kp2[2 * src + 1]);
+    std::vector<int64_t> first(nseg + 1, 0);  // first match of each segment
+    for (int s = 0; s < nseg; ++s) first[s + 1] = first[s] + segs[s].y;
+    auto fill = [&](int s0, int s1) {
+      for (int s = s0; s < s1; ++s) {
+        float4* dst = hpts + (size_t)segs[s].x * 32;
+        const int64_t src0 = first[s];
+        const int cnt = segs[s].y, padded = (cnt + 31) / 32 * 32;
+        for (int k = 0; k < cnt; ++k) {
+          const int64_t src = src0 + k;
+          dst[k] = make_float4((float)kp1[2 * src], (float)kp1[2 * src + 1], (float)kp2[2 * src], (float)kp2[2 * src + 1]);
+        }
+        for (int k = cnt; k < padded; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthreads = m_total > 200000 ? (int)(hw < 8 ? (hw ? hw : 1) : 8) : 1;
+    if (nthreads > nseg) nthreads = nseg > 0 ? nseg : 1;
+    if (nthreads <= 1) {
+      fill(0, nseg);
+    } else {  // segments split into contiguous blocks of roughly equal match counts
+      std::vector<std::thread> pool;
+      int s0 = 0;
+      for (int t = 0; t < nthreads; ++t) {
+        const int64_t target = m_total * (t + 1) / nthreads;
+        int s1 = s0;
+        while (s1 < nseg && first[s1 + 1] <= target) ++s1;
+        if (t == nthreads - 1) s1 = nseg;
+        pool.emplace_back(fill, s0, s1);
+        s0 = s1;
+      }
+      for (auto& th : pool) th.join();
     }
   }
   Matches* m = new (std::nothrow) Matches();
@@ -205,11 +245,18 @@ int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const
   m->frames = frames;
   m->height = height;
   m->width = width;
-  cudaError_t err = cudaMalloc(&m->pts, sizeof(float4) * (pts.size() ? pts.size() : 1));
-  if (err == cudaSuccess) err = cudaMalloc(&m->segs, sizeof(int4) * segs.size());
-  if (err == cudaSuccess && !pts.empty()) err = cudaMemcpyAsync(m->pts, pts.data(), sizeof(float4) * pts.size(), cudaMemcpyHostToDevice, st);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(m->segs, segs.data(), sizeof(int4) * segs.size(), cudaMemcpyHostToDevice, st);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(st);  // the host vectors die at return
+  void* dpts = nullptr;
+  void* dsegs = nullptr;
+  if (pool_take(ctx, &dpts, &m->pts_bytes, pts_bytes) != PDB_OK || pool_take(ctx, &dsegs, &m->segs_bytes, segs_bytes) != PDB_OK) {
+    pool_give(ctx, dpts, m->pts_bytes);
+    delete m;
+    return PDB_ERR_CUDA;
+  }
+  m->pts = static_cast<float4*>(dpts);
+  m->segs = static_cast<int4*>(dsegs);
+  cudaError_t err = cudaMemcpyAsync(m->pts, hpts, pts_bytes, cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(m->segs, hsegs, segs_bytes, cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);  // the staging buffer is reused by the next call
   if (err != cudaSuccess) {
     pdb_matches_free(reinterpret_cast<pdb_matches*>(m));
     return ctx->fail(PDB_ERR_CUDA, "match upload failed: %s", cudaGetErrorString(err));
@@ -221,8 +268,8 @@ int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const
 void pdb_matches_free(pdb_matches* pm) {
   if (!pm) return;
   Matches* m = reinterpret_cast<Matches*>(pm);
-  if (m->pts) cudaFree(m->pts);
-  if (m->segs) cudaFree(m->segs);
+  pool_give(m->ctx, m->pts, m->pts_bytes);  // back to the context's pool (cudaFree is slow and synchronising)
+  pool_give(m->ctx, m->segs, m->segs_bytes);
   delete m;
 }
 
@@ -261,9 +308,12 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   const size_t fixed = ggs_smem_fixed_bytes(max_frames);
   const size_t budget = ctx->smem_optin > fixed + 1024 ? ctx->smem_optin - fixed - 1024 : 0;
   const long long rounds_per_cta = (max_rounds + cpp - 1) / cpp + 1;
-  const bool resident = (size_t)rounds_per_cta * 512 <= budget;
+  // PDB_GGS_FORCE_STREAM=1 disables the shared-memory-resident mode (tests exercise the streaming ring with it)
+  const char* force_stream = getenv("PDB_GGS_FORCE_STREAM");
+  const bool resident = (size_t)rounds_per_cta * 512 <= budget && !(force_stream && force_stream[0] == '1');
   P.resident_rounds = resident ? (int)rounds_per_cta : 0;
-  const size_t smem = fixed + (resident ? (size_t)rounds_per_cta * 512 : 0);
+  P.ring = resident ? 0 : 1;
+  const size_t smem = fixed + (resident ? (size_t)rounds_per_cta * 512 : (size_t)kRingBytes);
   static size_t attr_bytes = 0;  // per instantiation
   if (smem > attr_bytes) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -166,6 +166,9 @@ void pdb_destroy(pdb_context* c) {
   if (ctx->ggs_ws) cudaFree(ctx->ggs_ws);
   if (ctx->den_ws) cudaFree(ctx->den_ws);
   if (ctx->stage) cudaFree(ctx->stage);
+  for (auto& b : ctx->pool) cudaFree(b.first);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  if (ctx->ggs_clock) cudaFree(ctx->ggs_clock);
   delete ctx;
 }
 

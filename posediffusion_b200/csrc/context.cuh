@@ -34,6 +34,10 @@ struct Context {
   bool profiling = false;
   struct Timed { cudaEvent_t a, b; int kind; };
   std::vector<Timed> timed;
+  // match ingestion: pinned host staging + a small pool of device buffers (cudaFree is slow and synchronising)
+  void* pin = nullptr;
+  size_t pin_bytes = 0;
+  std::vector<std::pair<void*, size_t>> pool;
   // staging for the host-buffer entry point
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -51,6 +55,7 @@ struct Context {
 
 struct Matches {
   Context* ctx = nullptr;
+  size_t pts_bytes = 0, segs_bytes = 0;
   float4* pts = nullptr;   // [rounds*32]
   int4* segs = nullptr;    // [nseg+1]
   int nseg = 0;
@@ -86,6 +91,26 @@ inline int ensure_buffer(Context* ctx, void** ptr, size_t* have, size_t need) {
   PDB_CUDA(ctx, cudaMalloc(ptr, grow));
   *have = grow;
   return PDB_OK;
+}
+
+inline int pool_take(Context* ctx, void** ptr, size_t* got, size_t need) {
+  int best = -1;
+  for (int i = 0; i < (int)ctx->pool.size(); ++i)
+    if (ctx->pool[i].second >= need && (best < 0 || ctx->pool[i].second < ctx->pool[best].second)) best = i;
+  if (best >= 0 && ctx->pool[best].second <= 2 * need + 4096) {
+    *ptr = ctx->pool[best].first;
+    *got = ctx->pool[best].second;
+    ctx->pool.erase(ctx->pool.begin() + best);
+    return PDB_OK;
+  }
+  PDB_CUDA(ctx, cudaMalloc(ptr, need));
+  *got = need;
+  return PDB_OK;
+}
+inline void pool_give(Context* ctx, void* ptr, size_t bytes) {
+  if (!ptr) return;
+  if (ctx->pool.size() < 16) ctx->pool.emplace_back(ptr, bytes);
+  else cudaFree(ptr);
 }
 
 }  // namespace pdb

@@ -201,10 +201,26 @@ PDB_HD void frame_adjoint(const float* p, const float* R, const float* gR, const
 }
 
 // One match of stage 1 (compute_sampson_distance :157-170 forward + the closed-form d err / d F').
-// F = F' row-major; acc[0..8] += G contribution, acc[9] += min(err, smax) (NaN passes, like torch.clamp),
-// acc[10] += valid err (only if kWithLoss); returns 1 if the match is valid (err < smax).
+// F = F' row-major.  Accumulators: acc[0..8] += G contribution, acc[9] += min(err, smax) (NaN passes, like
+// torch.clamp), acc[10] += valid err (only if kWithLoss), acc[11] += 1 per valid match (exact in fp32 below 2^24
+// per lane).  `inb` is false only for the padding lanes of a segment's last round (their coordinates are 0).
+//
+// Arithmetic is arranged for instruction count (this loop is the whole cost of the big configurations):
+//   t = top / bottom, err = top * t, a = 2 t, b = a t  (= 2 err / bottom), and validity enters as a 0/1 WEIGHT
+//   on `a` (not a select): 0 * (0/0) = NaN poisons the gradient exactly like the reference's autograd does for a
+//   diagonal pair, and 0 * finite = 0 drops invalid matches.
+PDB_HD float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));  // <= 1 ulp; rcp(0) = inf like the IEEE quotient
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+
 template <bool kWithLoss>
-PDB_HD int sampson_match(const float4 pt, const float* F, bool inb, float smax, float* acc) {
+PDB_HD void sampson_match(const float4 pt, const float* F, bool inb, float smax, float* acc) {
   const float u1 = pt.x, v1 = pt.y, u2 = pt.z, v2 = pt.w;
   const float l0 = fmaf(u1, F[0], fmaf(v1, F[3], F[6]));
   const float l1 = fmaf(u1, F[1], fmaf(v1, F[4], F[7]));
@@ -213,31 +229,28 @@ PDB_HD int sampson_match(const float4 pt, const float* F, bool inb, float smax, 
   const float r1 = fmaf(F[3], u2, fmaf(F[4], v2, F[5]));
   const float top = fmaf(l0, u2, fmaf(l1, v2, l2));
   const float bottom = fmaf(l0, l0, fmaf(l1, l1, fmaf(r0, r0, r1 * r1)));
-  const float inv = 1.0f / bottom;
-  const float err = top * top * inv;
+  const float t = top * fast_rcp(bottom);
+  const float err = top * t;
   const bool valid = inb && (err < smax);
-  // validity enters as a 0/1 weight (not a select) so that 0 * (0/0) poisons the gradient exactly like the
-  // reference's autograd does for a diagonal pair; padding lanes (inb == false) are removed by select.
   const float wgt = valid ? 1.f : 0.f;
-  float ca = wgt * (2.f * top * inv);
-  float cb = wgt * (2.f * err * inv);
-  ca = inb ? ca : 0.f;
-  cb = inb ? cb : 0.f;
+  const float a = wgt * (t + t);
+  const float nb = -(a * t);
   const float clamped = (err > smax) ? smax : err;
   acc[9] += inb ? clamped : 0.f;
   if (kWithLoss) acc[10] += valid ? err : 0.f;
-  const float w0 = fmaf(ca, u2, -cb * l0), w1 = fmaf(ca, v2, -cb * l1), w2 = ca;
-  const float c0 = cb * r0, c1 = cb * r1;
-  acc[0] += fmaf(u1, w0, -c0 * u2);
-  acc[1] += fmaf(u1, w1, -c0 * v2);
-  acc[2] += fmaf(u1, w2, -c0);
-  acc[3] += fmaf(v1, w0, -c1 * u2);
-  acc[4] += fmaf(v1, w1, -c1 * v2);
-  acc[5] += fmaf(v1, w2, -c1);
+  acc[11] += wgt;
+  // G_ij += x1_i (a x2_j - b lz_j) - b rz_i x2_j
+  const float w0 = fmaf(a, u2, nb * l0), w1 = fmaf(a, v2, nb * l1);
+  const float c0 = nb * r0, c1 = nb * r1;
+  acc[0] = fmaf(c0, u2, fmaf(u1, w0, acc[0]));
+  acc[1] = fmaf(c0, v2, fmaf(u1, w1, acc[1]));
+  acc[2] = fmaf(u1, a, acc[2]) + c0;
+  acc[3] = fmaf(c1, u2, fmaf(v1, w0, acc[3]));
+  acc[4] = fmaf(c1, v2, fmaf(v1, w1, acc[4]));
+  acc[5] = fmaf(v1, a, acc[5]) + c1;
   acc[6] += w0;
   acc[7] += w1;
-  acc[8] += w2;
-  return valid ? 1 : 0;
+  acc[8] += a;
 }
 
 // ---------------------------------------------------------------------------------------------

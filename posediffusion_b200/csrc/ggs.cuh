@@ -24,7 +24,9 @@ namespace pdb {
 constexpr int kGgsThreads = 512;
 constexpr int kGgsWarps = kGgsThreads / 32;
 constexpr int kGgsMaxSeg = 128;   // pair segments handled per chunk by one CTA
-constexpr int kGgsUnroll = 4;     // rounds (of 32 matches) in flight per warp
+constexpr int kGgsUnroll = 4;     // rounds (of 32 matches) per streaming chunk (2 KB)
+constexpr int kRingStages = 4;    // chunks in flight per warp in the bulk-async ring (8 KB per warp, 128 KB per CTA)
+constexpr int kRingBytes = kGgsWarps * kRingStages * kGgsUnroll * 512 + kGgsWarps * kRingStages * 8;
 constexpr int kAccTail = 4;       // {g_fx', g_fy', clamp_sum, valid error sum (eval mode)}
 constexpr int kAccPad = 32;        // each global accumulator sits in its own 128-byte line: 148 CTAs adding into 5 lines
                                   // serialise on a few L2 slices; one line per value spreads them over the whole L2
@@ -58,6 +60,7 @@ struct GgsParams {
   float alpha, lr, smax, momentum;
   double min_matches;
   int resident_rounds;  // rounds of 32 matches that fit the CTA's shared-memory match cache (0 = always stream)
+  int ring;             // 1: shared memory holds the bulk-async streaming ring (used when the slice is not resident)
 };
 
 constexpr int kGgsFixedFloatsPerFrame = 2 * 9 + 4 * 9 + 4 + 18 + 7;  // pose, vel, R, A, Rt, At, fl, inr, gAt|gRt, summed gradient
@@ -120,6 +123,16 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   const int wseg0 = (r_w1 > r_w0) ? seg_of_round(r_w0) : 0;
   const bool single_chunk = (seg_hi - seg_lo + 1) <= kGgsMaxSeg;
   const bool resident = (r_cta1 - r_cta0) <= P.resident_rounds;
+  const bool use_ring = !resident && single_chunk && P.ring;
+  // bulk-async ring of this warp: kRingStages chunks of kGgsUnroll rounds + one mbarrier per stage
+  const uint32_t ring_base = smem_u32(s_pts) + warp * (kRingStages * kGgsUnroll * 512);
+  const uint32_t ring_bar = smem_u32(s_pts) + kGgsWarps * kRingStages * kGgsUnroll * 512 + warp * (kRingStages * 8);
+  const float4* ring_ptr = s_pts + warp * (kRingStages * kGgsUnroll * 32);
+  unsigned ring_phase = 0;  // bit s = parity to wait for on stage s (warp-uniform, persists across iterations)
+  if (use_ring && lane == 0) {
+    for (int st = 0; st < kRingStages; ++st) mbar_init(ring_bar + st * 8, 1);
+    mbar_fence_init();
+  }
 
   for (int e = tid; e < N9; e += kGgsThreads) {
     s_pose[e] = pr.pose[e];
@@ -226,6 +239,80 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         }
         // ---- stage 1: stream the matches of this warp's rounds ----
         {
+          if (use_ring) {
+            const int nr_w = r_w1 - r_w0;
+            if (nr_w > 0) {
+              const int nch = (nr_w + kGgsUnroll - 1) / kGgsUnroll;
+              auto issue = [&](int c) {  // lane 0: request chunk c into stage c % kRingStages
+                const int st = c % kRingStages;
+                const int rounds_c = min(kGgsUnroll, nr_w - c * kGgsUnroll);
+                mbar_arrive_expect_tx(ring_bar + st * 8, rounds_c * 512);
+                bulk_copy_g2s(ring_base + st * (kGgsUnroll * 512), pr.pts + (size_t)(r_w0 + c * kGgsUnroll) * 32, rounds_c * 512,
+                              ring_bar + st * 8);
+              };
+              if (lane == 0)
+                for (int c = 0; c < min(kRingStages, nch); ++c) issue(c);
+              int s = wseg0;
+              int4 sd = s_seg[s - cs];
+              int seg_end = s_seg[s - cs + 1].x;
+              float Fm[9], g[16];
+              int nval = 0;
+              auto begin_segment = [&]() {
+                float mine = 0.f;
+                if (lane < 9 && sd.z != sd.w)
+                  mine = pair_F_entry(s_At + sd.z * 9, s_Rt + sd.z * 9, s_At + sd.w * 9, s_Rt + sd.w * 9, lane / 3, lane % 3);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Fm[k] = __shfl_sync(0xffffffffu, mine, k);
+                if (kEval && pr.dbg_F && lane < 9) pr.dbg_F[(size_t)s * 9 + lane] = mine;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) g[k] = 0.f;
+                nval = 0;
+              };
+              auto end_segment = [&]() {
+                nval = __reduce_add_sync(0xffffffffu, (int)g[11]);  // per-lane counts are exact small integers
+                const float tot = warp_reduce16(g, lane);
+                const int slot = warp_reduce16_slot(lane);
+                if (!(lane & 1) && slot < 11) atomicAdd(&s_sacc[(s - cs) * kSegAcc + slot], tot);
+                if (lane == 0 && nval) atomicAdd(&s_scnt[s - cs], nval);
+              };
+              begin_segment();
+              for (int c = 0; c < nch; ++c) {
+                const int st = c % kRingStages;
+                mbar_wait(ring_bar + st * 8, (ring_phase >> st) & 1u);
+                ring_phase ^= 1u << st;
+                const int q0 = r_w0 + c * kGgsUnroll;
+                if (q0 + kGgsUnroll <= r_w1 && q0 + kGgsUnroll <= seg_end && (q0 + kGgsUnroll - sd.x) * 32 <= sd.y) {
+                  // common case: the whole chunk lies inside the current pair segment and holds no padding rows ->
+                  // a branch-free body the compiler interleaves across the four matches
+                  float4 pt[kGgsUnroll];
+#pragma unroll
+                  for (int u = 0; u < kGgsUnroll; ++u) pt[u] = ring_ptr[(st * kGgsUnroll + u) * 32 + lane];
+#pragma unroll
+                  for (int u = 0; u < kGgsUnroll; ++u) sampson_match<kEval>(pt[u], Fm, true, P.smax, g);
+                } else {
+#pragma unroll
+                  for (int u = 0; u < kGgsUnroll; ++u) {
+                    const int q = q0 + u;
+                    if (q < r_w1) {        // warp-uniform
+                      if (q >= seg_end) {  // next pair segment (warp-uniform, rare)
+                        end_segment();
+                        ++s;
+                        sd = s_seg[s - cs];
+                        seg_end = s_seg[s - cs + 1].x;
+                        begin_segment();
+                      }
+                      const float4 pt = ring_ptr[(st * kGgsUnroll + u) * 32 + lane];
+                      const bool inb = (q - sd.x) * 32 + lane < sd.y;
+                      sampson_match<kEval>(pt, Fm, inb, P.smax, g);
+                    }
+                  }
+                }
+                __syncwarp();  // every lane has consumed the stage before it is refilled
+                if (lane == 0 && c + kRingStages < nch) issue(c + kRingStages);
+              }
+              end_segment();
+            }
+          } else {
           int s = max(cs, wseg0);
           int r = (s < ce) ? max(r_w0, s_seg[s - cs].x) : r_w1;
           while (s < ce && r < r_w1) {
@@ -249,35 +336,43 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             if (resident) {
               const float4* base = s_pts + (size_t)(r - r_cta0) * 32 + lane;
               const int nr = r_end - r;
-#pragma unroll 2
+#pragma unroll 4
               for (int q = 0; q < nr; ++q) {
                 const float4 pt = base[q * 32];
                 const bool inb = (r + q - seg_first) * 32 + lane < seg_count;
-                nval += sampson_match<kEval>(pt, Fm, inb, P.smax, g);
+                sampson_match<kEval>(pt, Fm, inb, P.smax, g);
               }
             } else {
+              // software-pipelined stream: the next batch of kGgsUnroll rounds (2 KB per warp) is requested before the
+              // current one is consumed, so up to 2*kGgsUnroll rounds per warp are in flight (HBM latency x bandwidth)
+              float4 cur[kGgsUnroll], nxt[kGgsUnroll];
+#pragma unroll
+              for (int u = 0; u < kGgsUnroll; ++u)
+                if (r + u < r_end) cur[u] = ld_stream_f4(pr.pts + (size_t)(r + u) * 32 + lane);
               for (; r < r_end; r += kGgsUnroll) {
-                float4 pt[kGgsUnroll];
 #pragma unroll
                 for (int u = 0; u < kGgsUnroll; ++u)
-                  if (r + u < r_end) pt[u] = ld_stream_f4(pr.pts + (size_t)(r + u) * 32 + lane);
+                  if (r + kGgsUnroll + u < r_end) nxt[u] = ld_stream_f4(pr.pts + (size_t)(r + kGgsUnroll + u) * 32 + lane);
 #pragma unroll
                 for (int u = 0; u < kGgsUnroll; ++u) {
                   if (r + u < r_end) {  // warp-uniform
                     const bool inb = (r + u - seg_first) * 32 + lane < seg_count;
-                    nval += sampson_match<kEval>(pt[u], Fm, inb, P.smax, g);
+                    sampson_match<kEval>(cur[u], Fm, inb, P.smax, g);
                   }
                 }
+#pragma unroll
+                for (int u = 0; u < kGgsUnroll; ++u) cur[u] = nxt[u];
               }
             }
             // warp reduction: 16 shuffles for the float slots, one redux for the count
+            nval = __reduce_add_sync(0xffffffffu, (int)g[11]);  // per-lane counts are exact small integers
             const float tot = warp_reduce16(g, lane);
             const int slot = warp_reduce16_slot(lane);
             if (!(lane & 1) && slot < 11) atomicAdd(&s_sacc[(s - cs) * kSegAcc + slot], tot);
-            nval = __reduce_add_sync(0xffffffffu, nval);
             if (lane == 0 && nval) atomicAdd(&s_scnt[s - cs], nval);
             r = r_end;
             ++s;
+          }
           }
         }
         __syncthreads();

@@ -37,8 +37,9 @@ extern "C" int geom_host_eval(const float* pose, int N, float height, float widt
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     for (int k = 0; k < count; ++k) {
       const float* p = pts + (size_t)(first + k) * 4;
-      nvalid += sampson_match<true>(make_float4(p[0], p[1], p[2], p[3]), F, true, smax, acc);
+      sampson_match<true>(make_float4(p[0], p[1], p[2], p[3]), F, true, smax, acc);
     }
+    nvalid += (long long)acc[11];
     total += count;
     clamp_sum += acc[9];
     loss_sum += acc[10];
@@ -85,8 +86,9 @@ extern "C" int geom_host_eval_folded(const float* pose, int N, float height, flo
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     for (int k = 0; k < count; ++k) {
       const float* p = pts + (size_t)(first + k) * 4;
-      nvalid += sampson_match<true>(make_float4(p[0], p[1], p[2], p[3]), F, true, smax, acc);
+      sampson_match<true>(make_float4(p[0], p[1], p[2], p[3]), F, true, smax, acc);
     }
+    nvalid += (long long)acc[11];
     total += count;
     clamp_sum += acc[9];
     loss_sum += acc[10];

@@ -253,6 +253,45 @@ def test_sampson_properties_at_full_size(ctx, dev):
     assert s0[1].item() == 380 * 256 and s0[0].item() < 1e-4
 
 
+@pytest.mark.parametrize("mode", ["resident", "stream"])
+def test_streaming_paths_agree(ctx, dev, mode, monkeypatch):
+    """The three ways stage 1 reads matches (shared-memory resident slice, bulk-async ring, plain global loads for
+    CTAs that own more than 128 pair segments) must give the same statistics and gradient."""
+    if mode == "stream":
+        monkeypatch.setenv("PDB_GGS_FORCE_STREAM", "1")
+    else:
+        monkeypatch.delenv("PDB_GGS_FORCE_STREAM", raising=False)
+    # (a) config-3-like shape
+    m, gt, start = syn.scene_matches(12, 300, seed=91, ragged=True)
+    pose = torch.from_numpy(start).to(dev)
+    grad, sc, _, _ = ctx.sampson_eval(ctx.pack_matches(m), pose)
+    c = s64.sampson_closed_form_f64(start, m)
+    assert abs(int(sc[1].item()) - c["n_valid"]) <= 2
+    np.testing.assert_allclose(grad.cpu().numpy(), c["grad"], rtol=0, atol=3e-4 * np.abs(c["grad"]).max())
+    # (b) pathological input: two pairs alternating row by row -> every match is its own segment (> 128 per CTA)
+    frames, rows = 4, 40000
+    rng = np.random.default_rng(5)
+    mm, _, st4 = syn.scene_matches(frames, rows // 12 + 1, seed=92)
+    pick = np.where((mm["i12"][:, 0] == 0) & (mm["i12"][:, 1] == 1))[0]
+    pick2 = np.where((mm["i12"][:, 0] == 2) & (mm["i12"][:, 1] == 3))[0]
+    n = min(len(pick), len(pick2))
+    order = np.stack([pick[:n], pick2[:n]], 1).reshape(-1)
+    inter = {"kp1": mm["kp1"][order], "kp2": mm["kp2"][order], "i12": mm["i12"][order], "img_shape": mm["img_shape"]}
+    pm = ctx.pack_matches(inter)
+    assert pm.segments == 2 * n
+    grad, sc, _, _ = ctx.sampson_eval(pm, torch.from_numpy(st4).to(dev))
+    c = s64.sampson_closed_form_f64(st4, inter)
+    assert abs(int(sc[1].item()) - c["n_valid"]) <= 2
+    np.testing.assert_allclose(grad.cpu().numpy(), c["grad"], rtol=0, atol=3e-4 * np.abs(c["grad"]).max())
+    # (c) a short five-phase run agrees between the modes through the oracle
+    cfg = syn.default_ggs_cfg()
+    cfg["iter_num"] = 6
+    p0 = torch.from_numpy(start)[None].to(dev).clone()
+    ctx.ggs([ctx.pack_matches(m)], p0, cfg, want_stats=False)
+    want = po.geometry_guided_sampling(torch.from_numpy(start)[None], 5, m, cfg)
+    np.testing.assert_allclose(p0[0].cpu().numpy(), want[0].numpy(), rtol=0, atol=3e-5 * np.abs(want).max().item())
+
+
 def test_matches_pack_validation(ctx):
     m = syn.uniform_matches(4, 8, seed=1)
     bad = dict(m)
