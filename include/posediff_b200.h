@@ -91,6 +91,12 @@ int pdb_profile_read(pdb_context* ctx, double* ggs_ms, int64_t* ggs_launches, do
  * out[cta][8] = {stage0, stage1+2a, stage2b, barrier, stage3, iterations, 0, 0}; enable != 0 arms it for single-sequence calls. */
 int pdb_debug_ggs_clocks(pdb_context* ctx, int32_t enable, int64_t* out, int32_t max_ctas);
 
+/* Test entry of the tensor-core linear layer (tcgen05.mma kind::tf32 fed by TMA; csrc/tc_linear.cuh):
+ * Y[S,O] = relu?(X[S,K] @ W[O,K]^T + bias + residual); K % 32 == 0, O % 64 == 0, fp32 in / out, TF32 products. */
+int pdb_debug_tc_linear(pdb_context* ctx, const float* x_dev, const float* w_dev, const float* bias_dev,
+                        const float* residual_dev, float* y_dev, int32_t S, int32_t O, int32_t K, int32_t relu,
+                        void* stream);
+
 /* DDPM schedule exactly as GaussianDiffusion.init_diff_hyper builds it (models/gaussian_diffuser.py:136-187;
  * "custom" = float64 linspace(beta_1, beta_T, 100), cumprod, cast to float32).  HOST-ONLY helper, needs no GPU:
  * out[100][8] = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,

@@ -65,6 +65,7 @@ EXPORTS = {
     "pdb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pdb_debug_ggs_clocks": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
+    "pdb_debug_tc_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "pdb_schedule_table": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "pdb_denoiser_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "pdb_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -204,6 +205,16 @@ class Context:
         out = np.zeros((256, 8), dtype=np.int64) if read else None
         self._ok(self.lib.pdb_debug_ggs_clocks(self.handle, int(enable), out.ctypes.data if read else None, 256), "pdb_debug_ggs_clocks")
         return out
+
+    def tc_linear(self, x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, relu: bool = False) -> torch.Tensor:
+        """Y = relu?(x @ w^T + bias + residual) on the tcgen05 tensor cores (TF32 products, fp32 accumulate)."""
+        S, K = x.shape
+        O = w.shape[0]
+        y = torch.empty(S, O, device=self.device)
+        self._ok(self.lib.pdb_debug_tc_linear(self.handle, x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                              residual.data_ptr() if residual is not None else None, y.data_ptr(), S, O, K,
+                                              int(relu), _stream_ptr(self.device)), "pdb_debug_tc_linear")
+        return y
 
     def sm_count(self) -> int:
         sm, a, b = C.c_int32(), C.c_int32(), C.c_int32()

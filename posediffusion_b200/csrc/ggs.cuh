@@ -336,11 +336,13 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             if (resident) {
               const float4* base = s_pts + (size_t)(r - r_cta0) * 32 + lane;
               const int nr = r_end - r;
+              // rounds without padding rows (all but possibly the segment's last one) run a select-free body
+              const int n_full = max(0, min(nr, seg_first + seg_count / 32 - r));
 #pragma unroll 4
-              for (int q = 0; q < nr; ++q) {
-                const float4 pt = base[q * 32];
+              for (int q = 0; q < n_full; ++q) sampson_match<kEval>(base[q * 32], Fm, true, P.smax, g);
+              for (int q = n_full; q < nr; ++q) {
                 const bool inb = (r + q - seg_first) * 32 + lane < seg_count;
-                sampson_match<kEval>(pt, Fm, inb, P.smax, g);
+                sampson_match<kEval>(base[q * 32], Fm, inb, P.smax, g);
               }
             } else {
               // software-pipelined stream: the next batch of kGgsUnroll rounds (2 KB per warp) is requested before the

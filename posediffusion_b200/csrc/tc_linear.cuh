@@ -1,0 +1,201 @@
+// Tensor-core linear layer for the batched denoiser (S = B*N >= 128 tokens per GPU, BASELINE config 4):
+//   Y[S, O] = epilogue( X[S, K] @ W[O, K]^T )
+// as tcgen05 (5th-gen tensor core) tiles fed by TMA, written directly in PTX for sm_100a:
+//   * TMA (`cp.async.bulk.tensor.2d`) stages 128-token x 32-float (128 B, SWIZZLE_128B) boxes of X and BN-feature boxes of
+//     W into a 4-deep shared-memory ring, completion counted on mbarriers;
+//   * one elected thread issues `tcgen05.mma.cta_group::1.kind::tf32` (fp32 operands read as TF32, fp32 accumulate) with
+//     shared-memory descriptors, 4 K-steps of 8 per stage; the 128 x BN fp32 accumulator lives in TMEM;
+//   * `tcgen05.commit` releases ring slots / signals the epilogue; 4 epilogue warps read TMEM with `tcgen05.ld`
+//     (32 lanes x 32 columns per instruction) and apply bias / folded LayerNorm / residual / ReLU on the way to HBM.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (one TMEM lane quarter each).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pdb {
+
+constexpr int kTcThreads = 192;
+constexpr int kTcStages = 4;
+constexpr int kTcBM = 128;  // tokens per tile  (UMMA M)
+constexpr int kTcBK = 32;   // floats per stage (128 bytes = one swizzle atom), 4 UMMA K-steps of 8
+
+struct TcEpilogue {
+  const float* bias;      // [O] or null
+  const float* residual;  // [S, ldr] or null (may alias Y: each element is read then written by the same thread)
+  int ldr;
+  const float* row_mean;  // folded LayerNorm: Y = rstd_s * (acc - mean_s * colsum_o) + bias_o   (all three or none)
+  const float* row_rstd;
+  const float* colsum;
+  float* Y;
+  int ldy;
+  int S, O, K;
+  int relu;
+};
+
+__host__ __device__ inline size_t tc_smem_bytes(int BN) {
+  return (size_t)kTcStages * (kTcBM * 128 + BN * 128) + 256 + 1024;  // ring + barriers + alignment slack
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4, LBO unused (1), SBO = 8 rows x
+// 128 B = 1024 B between core-matrix groups, descriptor version 1, layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor: D = F32 (bits 4-5 = 1), A/B = TF32 (2) K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcEpilogue E) {
+  static_assert(BN == 64 || BN == 128, "feature tile");
+  extern __shared__ unsigned char tc_smem_raw[];
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  constexpr uint32_t kABytes = kTcBM * 128, kBBytes = BN * 128, kStageBytes = kABytes + kBBytes;
+  const uint32_t bar_base = base + kTcStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (kTcStages + s) * 8; };
+  const uint32_t tmem_full_bar = bar_base + 2 * kTcStages * 8;
+  const uint32_t tmem_slot = tmem_full_bar + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
+  const int num_kb = E.K / kTcBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_arrive_expect_tx(full_bar(s), kStageBytes);
+        tma_load_2d(base + s * kStageBytes, &map_x, kb * kTcBK, m0, full_bar(s));
+        tma_load_2d(base + s * kStageBytes + kABytes, &map_w, kb * kTcBK, n0, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_tf32(kTcBM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = umma_desc_k128(base + s * kStageBytes);
+        const uint64_t db = umma_desc_k128(base + s * kStageBytes + kABytes);
+#pragma unroll
+        for (int k = 0; k < kTcBK / 8; ++k)  // advance 8 floats = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
+          umma_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(empty_bar(s));  // frees the slot once the MMAs that read it have retired
+      }
+      umma_commit(tmem_full_bar);   // accumulator complete
+    }
+  } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < E.S;
+    float mean = 0.f, rstd = 1.f;
+    if (E.colsum && row_ok) {
+      mean = E.row_mean[row];
+      rstd = E.row_rstd[row];
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      if (row_ok) {
+        float* yrow = E.Y + (size_t)row * E.ldy + n0 + c0;
+        const float* rrow = E.residual ? E.residual + (size_t)row * E.ldr + n0 + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int col = n0 + c0 + j + t;
+            float x = v[j + t];
+            if (E.colsum) x = rstd * (x - mean * __ldg(E.colsum + col));
+            if (E.bias) x += __ldg(E.bias + col);
+            o[t] = x;
+          }
+          if (rrow) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+          }
+          if (E.relu) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
+          }
+          *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+}  // namespace pdb
