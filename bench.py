@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU GGS iterations in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--denoiser-engine", default="auto", choices=["auto", "fp32", "tf32"],
+                    help="auto = exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tiles (TF32) at or above")
     args = ap.parse_args()
     frames, per_pair, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -191,6 +193,7 @@ def main():
     den.load_state_dict(syn.random_denoiser_state(args.seed), strict=True)
     den = den.to(dev)
     ctx = den.native_context()
+    ctx.set_denoiser_engine(args.denoiser_engine)
     cfg = syn.default_ggs_cfg()
     cfg["verbose"] = False
     start_step = cfg["start_step"] if per_pair else 0
@@ -276,8 +279,9 @@ def main():
         "metric": "diffusion steps/sec (20-frame seq, GGS on)" if args.workload == "cfg3" else f"diffusion steps/sec ({args.workload})",
         "value": value, "unit": "diffusion steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "sequences_per_gpu": B, "timesteps": T_STEPS,
+        "dtype": "f32" if (args.denoiser_engine == "fp32" or (args.denoiser_engine == "auto" and B * frames < 128)) else "f32 (GGS, residual stream) + tf32 tensor-core products (denoiser projections)",
+        "data": "synthetic",
+        "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "sequences_per_gpu": B, "denoiser_engine": args.denoiser_engine, "timesteps": T_STEPS,
                    "parallelism": f"sequences sharded over {world} GPU(s), final all-gather of poses only",
                    "l2": "flushed between timed loops (256 MiB write); within a loop the 12.45 MB match set is deliberately L2-resident",
                    "weights": "random init (reference init law), z ~ N(0,1), uniform-random correspondences"},

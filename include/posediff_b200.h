@@ -91,6 +91,10 @@ int pdb_profile_read(pdb_context* ctx, double* ggs_ms, int64_t* ggs_launches, do
  * out[cta][8] = {stage0, stage1+2a, stage2b, barrier, stage3, iterations, 0, 0}; enable != 0 arms it for single-sequence calls. */
 int pdb_debug_ggs_clocks(pdb_context* ctx, int32_t enable, int64_t* out, int32_t max_ctas);
 
+/* Denoiser engine: 0 = auto (exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tensor-core tiles with TF32
+ * products at or above), 1 = always fp32, 2 = always tensor cores. */
+int pdb_denoiser_engine(pdb_context* ctx, int32_t mode);
+
 /* Test entry of the tensor-core linear layer (tcgen05.mma kind::tf32 fed by TMA; csrc/tc_linear.cuh):
  * Y[S,O] = relu?(X[S,K] @ W[O,K]^T + bias + residual); K % 32 == 0, O % 64 == 0, fp32 in / out, TF32 products. */
 int pdb_debug_tc_linear(pdb_context* ctx, const float* x_dev, const float* w_dev, const float* bias_dev,

@@ -65,6 +65,7 @@ EXPORTS = {
     "pdb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pdb_debug_ggs_clocks": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
+    "pdb_denoiser_engine": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_debug_tc_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "pdb_schedule_table": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "pdb_denoiser_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
@@ -205,6 +206,10 @@ class Context:
         out = np.zeros((256, 8), dtype=np.int64) if read else None
         self._ok(self.lib.pdb_debug_ggs_clocks(self.handle, int(enable), out.ctypes.data if read else None, 256), "pdb_debug_ggs_clocks")
         return out
+
+    def set_denoiser_engine(self, mode: str = "auto"):
+        """'auto' (fp32 kernel below 128 tokens, tensor cores above), 'fp32' or 'tf32'."""
+        self._ok(self.lib.pdb_denoiser_engine(self.handle, {"auto": 0, "fp32": 1, "tf32": 2}[mode]), "pdb_denoiser_engine")
 
     def tc_linear(self, x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, relu: bool = False) -> torch.Tensor:
         """Y = relu?(x @ w^T + bias + residual) on the tcgen05 tensor cores (TF32 products, fp32 accumulate)."""

@@ -5,6 +5,7 @@
 
 #include "context.cuh"
 #include "denoiser.cuh"
+#include "weights.cuh"
 
 using namespace pdb;
 
@@ -12,12 +13,10 @@ namespace pdb {
 int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* pose_dev, const pdb_ggs_config* cfg,
                 pdb_ggs_stats* stats_dev, cudaStream_t st);
 
-struct DenoiserWeights {
-  float* arena = nullptr;
-  size_t arena_floats = 0;
-  DenoiserDev dev = {};
-};
+int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st);
 }  // namespace pdb
+
+constexpr int kTcMinTokens = 128;
 
 namespace {
 
@@ -50,6 +49,38 @@ __global__ void naive_linear_kernel(const float* __restrict__ X, int S, int K, c
   if (bias) acc += bias[o];
   if (silu) acc = acc / (1.0f + expf(-acc));
   Y[idx] = acc;
+}
+
+// W[O][ldw] column window -> dense row-major [O][Kpad] (zero padded): operands of the tensor-core engine
+__global__ void copy_cols_kernel(const float* __restrict__ W, int O, int ldw, int c0, int Kuse, int Kpad, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= O * Kpad) return;
+  const int o = idx / Kpad, k = idx - o * Kpad;
+  out[idx] = (k < Kuse) ? W[(size_t)o * ldw + c0 + k] : 0.f;
+}
+// LayerNorm folded into the following Linear:  LN(x) W^T + b = rstd (x Wf^T - mean colsum) + biasf  with
+// Wf = gamma * W (column-wise), colsum_o = sum_k Wf[o][k], biasf_o = b_o + sum_k beta_k W[o][k].  One block per output row.
+__global__ void fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, int K, float* __restrict__ Wf, float* __restrict__ colsum,
+                               float* __restrict__ biasf) {
+  const int o = blockIdx.x;
+  float cs = 0.f, bs = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float w = W[(size_t)o * K + k];
+    const float wf = w * gamma[k];
+    Wf[(size_t)o * K + k] = wf;
+    cs += wf;
+    bs += w * beta[k];
+  }
+  __shared__ float red[2][4];
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cs; red[1][threadIdx.x >> 5] = bs; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    colsum[o] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    biasf[o] = bias[o] + red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  }
 }
 
 const int kShape[6][2] = {{128, 256}, {128, 0}, {128, 128}, {128, 0}, {512, 702}, {512, 0}};
@@ -127,6 +158,10 @@ int enqueue_denoiser(Context* ctx, DenoiserRun run, cudaStream_t st) {
   if (run.t_hi >= kT || run.t_lo < 0 || run.t_hi < run.t_lo) return ctx->fail(PDB_ERR_INVALID, "bad timestep range");
   const int S = run.batch * run.frames;
   run.tokens = S;
+  // engine: exact-fp32 persistent kernel below kTcMinTokens tokens (latency bound), tcgen05/TMA tiles (TF32 products) at or
+  // above it (throughput bound).  ctx->denoiser_engine: 0 auto, 1 force fp32, 2 force tensor cores.
+  const bool use_tc = ctx->denoiser_engine == 2 || (ctx->denoiser_engine == 0 && S >= kTcMinTokens);
+  if (use_tc) return enqueue_denoiser_tc(ctx, run, st);
   const size_t need = sizeof(float) * denoiser_ws_floats(S);
   if (int rc = ensure_buffer(ctx, &ctx->den_ws, &ctx->den_ws_bytes, need)) return rc;
   float* ws = static_cast<float*>(ctx->den_ws);
@@ -161,6 +196,8 @@ void pdb_destroy(pdb_context* c) {
   cudaSetDevice(ctx->device);
   if (ctx->weights) {
     if (ctx->weights->arena) cudaFree(ctx->weights->arena);
+    if (ctx->weights->raw) cudaFree(ctx->weights->raw);
+    if (ctx->weights->tc_arena) cudaFree(ctx->weights->tc_arena);
     delete ctx->weights;
   }
   if (ctx->ggs_ws) cudaFree(ctx->ggs_ws);
@@ -301,10 +338,43 @@ int pdb_denoiser_load(pdb_context* c, const float* const* tensors, int32_t count
     cudaMemcpyAsync(A + o_sched, sched, sizeof(sched), cudaMemcpyHostToDevice, st);
     cudaStreamSynchronize(st);
   }
-  err = cudaStreamSynchronize(st);
+  // ---- operands of the tensor-core engine: row-major weights, LayerNorm gamma/beta folded into QKV and FF1 ----
+  {
+    size_t tt = 0;
+    auto take2 = [&](size_t n) { size_t at = tt; tt += (n + 63) / 64 * 64; return at; };
+    const size_t t_wx = take2((size_t)kDM * kPoseEmbPad), t_wz = take2((size_t)kDM * kZ);
+    size_t t_l[kLayers][6];
+    for (int l = 0; l < kLayers; ++l) {
+      t_l[l][0] = take2((size_t)3 * kDM * kDM); t_l[l][1] = take2(3 * kDM); t_l[l][2] = take2(3 * kDM);
+      t_l[l][3] = take2((size_t)kFF * kDM);     t_l[l][4] = take2(kFF);     t_l[l][5] = take2(kFF);
+    }
+    err = cudaMalloc(&w->tc_arena, sizeof(float) * tt);
+    if (err == cudaSuccess) {
+      float* T = w->tc_arena;
+      copy_cols_kernel<<<(kDM * kPoseEmbPad + 255) / 256, 256, 0, st>>>(raw + off[4], kDM, kFirstIn, 0, kPoseEmb, kPoseEmbPad, T + t_wx);
+      copy_cols_kernel<<<(kDM * kZ + 255) / 256, 256, 0, st>>>(raw + off[4], kDM, kFirstIn, kPoseEmb + kTEmb, kZ, kZ, T + t_wz);
+      TcWeights& tc = w->tc;
+      tc.wx = T + t_wx; tc.wz = T + t_wz; tc.w_pivot = A + o_piv; tc.b_first = A + o_bf; tc.tproj = A + o_tproj;
+      tc.wlast0 = raw + off[tb + 0]; tc.blast0 = raw + off[tb + 1];
+      for (int l = 0; l < kLayers; ++l) {
+        const int b = 6 + 12 * l;
+        fold_ln_kernel<<<3 * kDM, 128, 0, st>>>(raw + off[b + 0], raw + off[b + 1], raw + off[b + 8], raw + off[b + 9], kDM,
+                                              T + t_l[l][0], T + t_l[l][1], T + t_l[l][2]);
+        fold_ln_kernel<<<kFF, 128, 0, st>>>(raw + off[b + 4], raw + off[b + 5], raw + off[b + 10], raw + off[b + 11], kDM,
+                                          T + t_l[l][3], T + t_l[l][4], T + t_l[l][5]);
+        TcLayer& L = tc.layer[l];
+        L.wqkv = T + t_l[l][0]; L.colsum_qkv = T + t_l[l][1]; L.bias_qkv = T + t_l[l][2];
+        L.wout = raw + off[b + 2]; L.bout = raw + off[b + 3];
+        L.wff1 = T + t_l[l][3]; L.colsum_ff1 = T + t_l[l][4]; L.bias_ff1 = T + t_l[l][5];
+        L.wff2 = raw + off[b + 6]; L.bff2 = raw + off[b + 7];
+      }
+    }
+  }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
   if (err == cudaSuccess) err = cudaGetLastError();
-  cudaFree(raw);
   if (err != cudaSuccess) {
+    cudaFree(raw);
+    if (w->tc_arena) cudaFree(w->tc_arena);
     cudaFree(w->arena);
     delete w;
     return ctx->fail(PDB_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(err));
@@ -331,8 +401,11 @@ int pdb_denoiser_load(pdb_context* c, const float* const* tensors, int32_t count
   d.ln_last_b = A + o_lb;
   d.w_last3 = A + o_w3;
   d.b_last3 = A + o_b3;
+  w->raw = raw;
   if (ctx->weights) {
     cudaFree(ctx->weights->arena);
+    if (ctx->weights->raw) cudaFree(ctx->weights->raw);
+    if (ctx->weights->tc_arena) cudaFree(ctx->weights->tc_arena);
     delete ctx->weights;
   }
   ctx->weights = w;

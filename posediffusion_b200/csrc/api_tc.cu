@@ -84,3 +84,136 @@ extern "C" int pdb_debug_tc_linear(pdb_context* c, const float* x_dev, const flo
   E.relu = relu;
   return enqueue_tc_linear(ctx, x_dev, w_dev, E, static_cast<cudaStream_t>(stream));
 }
+
+// ================================================================================================
+// Tensor-core denoiser engine (S >= 128 tokens per GPU): one kernel per stage, projections on tcgen05/TMA tiles.
+// Same maths as denoiser_kernel (csrc/denoiser.cuh); LayerNorm is folded into the QKV / FF1 weights at load time and
+// applied in the GEMM epilogue from per-row statistics.  TF32 products, fp32 accumulate / residual stream.
+// ================================================================================================
+#include "weights.cuh"
+
+namespace {
+
+__global__ void embed_kernel(const float* __restrict__ x, float* __restrict__ emb, int S) {  // [S,9] -> [S,256] harmonic features
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * kPoseEmbPad) return;
+  const int s = i / kPoseEmbPad, col = i - s * kPoseEmbPad;
+  float v = 0.f;
+  if (col < 180) {
+    const int j = col < 90 ? col : col - 90;
+    const int c = j / 10, k = j - c * 10;
+    const float arg = x[s * 9 + c] * (float)(1 << k);
+    v = col < 90 ? sinf(arg) : cosf(arg);
+  } else if (col < kPoseEmb) {
+    v = x[s * 9 + (col - 180)];
+  }
+  emb[i] = v;
+}
+__global__ void pivot_add_kernel(float* __restrict__ zproj, const float* __restrict__ w_pivot, int batch, int frames) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // first frame of every sequence gets the pivot column
+  if (i < batch * kDM) zproj[(size_t)(i / kDM) * frames * kDM + (i % kDM)] += w_pivot[i % kDM];
+}
+__global__ void row_stats_kernel(const float* __restrict__ h, float* __restrict__ mean, float* __restrict__ rstd, int S) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= S) return;
+  const float4* p = reinterpret_cast<const float4*>(h + (size_t)row * kDM);
+  float4 v[4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = p[lane + 32 * i];
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float m = warp_sum(sum) * (1.0f / kDM);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[i].x - m, b = v[i].y - m, c = v[i].z - m, d = v[i].w - m;
+    sq += a * a + b * b + c * c + d * d;
+  }
+  const float var = warp_sum(sq) * (1.0f / kDM);
+  if (lane == 0) {
+    mean[row] = m;
+    rstd[row] = 1.0f / sqrtf(var + kLnEps);
+  }
+}
+__global__ void __launch_bounds__(kDenThreads) attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int frames) {
+  extern __shared__ __align__(16) float att_smem[];
+  const int chunks = (frames + kDenWarps - 1) / kDenWarps;
+  const int item = blockIdx.x;
+  attention_item(att_smem, qkv, att, item / (kHeads * chunks), (item / chunks) % kHeads, item % chunks, frames);
+}
+__global__ void __launch_bounds__(kDenThreads) tail_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R, int t, int last) {
+  const int s = blockIdx.x * kDenWarps + (threadIdx.x >> 5);
+  if (s < R.tokens) tail_token(W, R, s, t, last != 0);
+}
+
+}  // namespace
+
+namespace pdb {
+
+int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
+  const DenoiserWeights* w = ctx->weights;
+  const TcWeights& T = w->tc;
+  const int S = run.tokens, B = run.batch, N = run.frames;
+  const size_t need = sizeof(float) * (denoiser_ws_floats(S) + (size_t)S * (kPoseEmbPad + 2) + 64);
+  if (int rc = ensure_buffer(ctx, &ctx->den_ws, &ctx->den_ws_bytes, need)) return rc;
+  float* ws = static_cast<float*>(ctx->den_ws) + 64;
+  run.zproj = ws; ws += (size_t)S * kDM;
+  run.h = ws;     ws += (size_t)S * kDM;
+  run.qkv = ws;   ws += (size_t)S * 3 * kDM;
+  run.att = ws;   ws += (size_t)S * kDM;
+  run.ff = ws;    ws += (size_t)S * kFF;
+  run.u = ws;     ws += (size_t)S * kHid;
+  float* emb = ws; ws += (size_t)S * kPoseEmbPad;
+  float* mean = ws; ws += S;
+  float* rstd = ws;
+  auto lin = [&](const float* X, const float* Wm, int O, int K, const float* bias, const float* residual, int ldr,
+                 const float* colsum, float* Y, int relu) {
+    TcEpilogue E = {};
+    E.bias = bias; E.residual = residual; E.ldr = ldr;
+    E.colsum = colsum; E.row_mean = colsum ? mean : nullptr; E.row_rstd = colsum ? rstd : nullptr;
+    E.Y = Y; E.ldy = O; E.S = S; E.O = O; E.K = K; E.relu = relu;
+    return enqueue_tc_linear(ctx, X, Wm, E, st);
+  };
+  const size_t att_smem = sizeof(float) * ((size_t)N * (kHD + 4) + (size_t)N * kHD + 2 * kDenWarps * kHD) + 64;
+  static size_t att_attr = 0;
+  if (att_smem > att_attr) {
+    PDB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+    att_attr = att_smem;
+  }
+  const int chunks = (N + kDenWarps - 1) / kDenWarps;
+  if (run.compute_zproj) {
+    if (int rc = lin(run.z, T.wz, kDM, kZ, T.b_first, nullptr, 0, nullptr, run.zproj, 0)) return rc;
+    pivot_add_kernel<<<(B * kDM + 255) / 256, 256, 0, st>>>(run.zproj, T.w_pivot, B, N);
+    ctx->launches += 1;
+  }
+  for (int t = run.t_hi; t >= run.t_lo; --t) {
+    embed_kernel<<<(S * kPoseEmbPad + 255) / 256, 256, 0, st>>>(run.x, emb, S);
+    if (int rc = lin(emb, T.wx, kDM, kPoseEmbPad, T.tproj + (size_t)t * kDM, run.zproj, kDM, nullptr, run.h, 0)) return rc;
+    for (int l = 0; l < kLayers; ++l) {
+      const TcLayer& L = T.layer[l];
+      row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(run.h, mean, rstd, S);
+      if (int rc = lin(run.h, L.wqkv, 3 * kDM, kDM, L.bias_qkv, nullptr, 0, L.colsum_qkv, run.qkv, 0)) return rc;
+      attention_kernel<<<B * kHeads * chunks, kDenThreads, att_smem, st>>>(run.qkv, run.att, N);
+      if (int rc = lin(run.att, L.wout, kDM, kDM, L.bout, run.h, kDM, nullptr, run.h, 0)) return rc;
+      row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(run.h, mean, rstd, S);
+      if (int rc = lin(run.h, L.wff1, kFF, kDM, L.bias_ff1, nullptr, 0, L.colsum_ff1, run.ff, 1)) return rc;
+      if (int rc = lin(run.ff, L.wff2, kDM, kFF, L.bff2, run.h, kDM, nullptr, run.h, 0)) return rc;
+      ctx->launches += 3;
+    }
+    if (int rc = lin(run.h, T.wlast0, kHid, kDM, T.blast0, nullptr, 0, nullptr, run.u, 0)) return rc;
+    tail_kernel<<<(S + kDenWarps - 1) / kDenWarps, kDenThreads, 0, st>>>(w->dev, run, t, t == run.t_lo);
+    ctx->launches += 2;
+  }
+  PDB_CUDA(ctx, cudaGetLastError());
+  return PDB_OK;
+}
+
+}  // namespace pdb
+
+extern "C" int pdb_denoiser_engine(pdb_context* c, int32_t mode) {
+  if (!c || mode < 0 || mode > 2) return PDB_ERR_INVALID;
+  reinterpret_cast<Context*>(c)->denoiser_engine = mode;
+  return PDB_OK;
+}

@@ -30,6 +30,7 @@ struct Context {
   // stage timing probe of the GGS kernel (debug): [ctas][8] cycle sums
   long long* ggs_clock = nullptr;
   int ggs_clock_ctas = 0;
+  int denoiser_engine = 0;  // 0 auto, 1 fp32 persistent kernel, 2 tcgen05/TMA tiles (TF32)
   // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser
   bool profiling = false;
   struct Timed { cudaEvent_t a, b; int kind; };

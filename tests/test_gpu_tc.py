@@ -33,3 +33,38 @@ def test_tc_linear_matches_fp32(ctx, S, O, K, epi):
     assert err <= 2e-3 * scale, (err, scale)
     # and it is really TF32-accurate, not garbage that happens to be small: correlation with the fp64 result
     assert torch.corrcoef(torch.stack([y.double().flatten(), ref.flatten()]))[0, 1].item() > 0.99999
+
+
+TRANSFORMER = dict(d_model=512, nhead=4, dim_feedforward=1024, num_encoder_layers=8, dropout=0.1, batch_first=True, norm_first=True)
+
+
+@pytest.mark.parametrize("B,N", [(8, 20), (1, 20), (2, 80)])
+def test_tensor_core_denoiser_engine_vs_fp32_engine_and_oracle(ctx, B, N):
+    """The tcgen05/TMA engine (TF32 products, LayerNorm folded into the GEMM epilogue) against the exact-fp32 engine
+    and the CPU oracle on the same inputs.  Tolerance 5e-3 absolute on eps (values O(0.1..1))."""
+    import posediffusion_b200 as pdb
+    from oracle import pose_oracle as po
+    from posediffusion_b200 import synthetic as syn
+
+    state = syn.random_denoiser_state(5, 0.05)
+    den = pdb.Denoiser(TRANSFORMER=TRANSFORMER)
+    den.load_state_dict(state, strict=True)
+    den = den.to("cuda")
+    c = den.native_context()
+    g = torch.Generator().manual_seed(B * 100 + N)
+    x = torch.randn(B, N, 9, generator=g) * 1.5
+    z = torch.randn(B, N, 384, generator=g)
+    t = torch.full((B,), 23, dtype=torch.long)
+    try:
+        c.set_denoiser_engine("fp32")
+        exact = den(x.cuda(), t.cuda(), z.cuda()).cpu()
+        c.set_denoiser_engine("tf32")
+        fast = den(x.cuda(), t.cuda(), z.cuda()).cpu()
+    finally:
+        c.set_denoiser_engine("auto")
+    with torch.no_grad():
+        want = po.build_denoiser(state)(x, t, z)
+    assert (exact - want).abs().max().item() < 5e-5
+    err = (fast - want).abs().max().item()
+    assert err < 5e-3, err
+    assert err > 0  # it really took the TF32 path
