@@ -212,14 +212,14 @@ PDB_HD void frame_adjoint(const float* p, const float* R, const float* gR, const
 PDB_HD float fast_rcp(float x) {
 #ifdef __CUDA_ARCH__
   float r;
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));  // <= 1 ulp; rcp(0) = inf like the IEEE quotient
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RCP, <= 1 ulp; rcp(0) = inf like the IEEE quotient (denormal x -> inf)
   return r;
 #else
   return 1.0f / x;
 #endif
 }
 
-template <bool kWithLoss>
+template <bool kWithLoss, int kStride = 1>
 PDB_HD void sampson_match(const float4 pt, const float* F, bool inb, float smax, float* acc) {
   const float u1 = pt.x, v1 = pt.y, u2 = pt.z, v2 = pt.w;
   const float l0 = fmaf(u1, F[0], fmaf(v1, F[3], F[6]));
@@ -236,21 +236,21 @@ PDB_HD void sampson_match(const float4 pt, const float* F, bool inb, float smax,
   const float a = wgt * (t + t);
   const float nb = -(a * t);
   const float clamped = (err > smax) ? smax : err;
-  acc[9] += inb ? clamped : 0.f;
-  if (kWithLoss) acc[10] += valid ? err : 0.f;
-  acc[11] += wgt;
+  acc[9 * kStride] += inb ? clamped : 0.f;
+  if (kWithLoss) acc[10 * kStride] += valid ? err : 0.f;
+  acc[11 * kStride] += wgt;
   // G_ij += x1_i (a x2_j - b lz_j) - b rz_i x2_j
   const float w0 = fmaf(a, u2, nb * l0), w1 = fmaf(a, v2, nb * l1);
   const float c0 = nb * r0, c1 = nb * r1;
-  acc[0] = fmaf(c0, u2, fmaf(u1, w0, acc[0]));
-  acc[1] = fmaf(c0, v2, fmaf(u1, w1, acc[1]));
-  acc[2] = fmaf(u1, a, acc[2]) + c0;
-  acc[3] = fmaf(c1, u2, fmaf(v1, w0, acc[3]));
-  acc[4] = fmaf(c1, v2, fmaf(v1, w1, acc[4]));
-  acc[5] = fmaf(v1, a, acc[5]) + c1;
-  acc[6] += w0;
-  acc[7] += w1;
-  acc[8] += a;
+  acc[0 * kStride] = fmaf(c0, u2, fmaf(u1, w0, acc[0 * kStride]));
+  acc[1 * kStride] = fmaf(c0, v2, fmaf(u1, w1, acc[1 * kStride]));
+  acc[2 * kStride] = fmaf(u1, a, acc[2 * kStride]) + c0;
+  acc[3 * kStride] = fmaf(c1, u2, fmaf(v1, w0, acc[3 * kStride]));
+  acc[4 * kStride] = fmaf(c1, v2, fmaf(v1, w1, acc[4 * kStride]));
+  acc[5 * kStride] = fmaf(v1, a, acc[5 * kStride]) + c1;
+  acc[6 * kStride] += w0;
+  acc[7 * kStride] += w1;
+  acc[8 * kStride] += a;
 }
 
 // ---------------------------------------------------------------------------------------------

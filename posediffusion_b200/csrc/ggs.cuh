@@ -72,6 +72,42 @@ __host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
   return (bytes + 127) / 128 * 128;
 }
 
+// Two matches per instruction: Blackwell's packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2) halves the issue slots of the
+// arithmetic that dominates stage 1.  Same formulas as `sampson_match` (geom.cuh) for two in-bounds rows A and B of the
+// same pair; acc2[k] holds separate partial sums for the two rows (merged at the segment end).
+__device__ __forceinline__ void sampson_match2(const float4 A, const float4 B, const float* __restrict__ F, float smax,
+                                               float2* __restrict__ acc2) {
+  float2 F2[9];  // (F'[k], F'[k]): the packed pipe reads a scalar register as a broadcast pair (R.F32 operand form)
+#pragma unroll
+  for (int k = 0; k < 9; ++k) F2[k] = make_float2(F[k], F[k]);
+  const float2 u1 = make_float2(A.x, B.x), v1 = make_float2(A.y, B.y), u2 = make_float2(A.z, B.z), v2 = make_float2(A.w, B.w);
+  const float2 l0 = __ffma2_rn(u1, F2[0], __ffma2_rn(v1, F2[3], F2[6]));
+  const float2 l1 = __ffma2_rn(u1, F2[1], __ffma2_rn(v1, F2[4], F2[7]));
+  const float2 l2 = __ffma2_rn(u1, F2[2], __ffma2_rn(v1, F2[5], F2[8]));
+  const float2 r0 = __ffma2_rn(F2[0], u2, __ffma2_rn(F2[1], v2, F2[2]));
+  const float2 r1 = __ffma2_rn(F2[3], u2, __ffma2_rn(F2[4], v2, F2[5]));
+  const float2 top = __ffma2_rn(l0, u2, __ffma2_rn(l1, v2, l2));
+  const float2 bottom = __ffma2_rn(l0, l0, __ffma2_rn(l1, l1, __ffma2_rn(r0, r0, __fmul2_rn(r1, r1))));
+  const float2 t = __fmul2_rn(top, make_float2(fast_rcp(bottom.x), fast_rcp(bottom.y)));
+  const float2 err = __fmul2_rn(top, t);
+  const float2 wgt = make_float2(err.x < smax ? 1.f : 0.f, err.y < smax ? 1.f : 0.f);
+  const float2 a = __fmul2_rn(wgt, __fadd2_rn(t, t));
+  const float2 nb = __fmul2_rn(a, make_float2(-t.x, -t.y));
+  acc2[9] = __fadd2_rn(acc2[9], make_float2(err.x > smax ? smax : err.x, err.y > smax ? smax : err.y));
+  acc2[11] = __fadd2_rn(acc2[11], wgt);
+  const float2 w0 = __ffma2_rn(a, u2, __fmul2_rn(nb, l0)), w1 = __ffma2_rn(a, v2, __fmul2_rn(nb, l1));
+  const float2 c0 = __fmul2_rn(nb, r0), c1 = __fmul2_rn(nb, r1);
+  acc2[0] = __ffma2_rn(c0, u2, __ffma2_rn(u1, w0, acc2[0]));
+  acc2[1] = __ffma2_rn(c0, v2, __ffma2_rn(u1, w1, acc2[1]));
+  acc2[2] = __fadd2_rn(__ffma2_rn(u1, a, acc2[2]), c0);
+  acc2[3] = __ffma2_rn(c1, u2, __ffma2_rn(v1, w0, acc2[3]));
+  acc2[4] = __ffma2_rn(c1, v2, __ffma2_rn(v1, w1, acc2[4]));
+  acc2[5] = __fadd2_rn(__ffma2_rn(v1, a, acc2[5]), c1);
+  acc2[6] = __fadd2_rn(acc2[6], w0);
+  acc2[7] = __fadd2_rn(acc2[7], w1);
+  acc2[8] = __fadd2_rn(acc2[8], a);
+}
+
 // One CTA of the group that owns one sequence.  See the file header for the stage structure.
 // `resident_rounds` > 0: the CTA's whole slice of matches (<= resident_rounds rounds) is staged in shared memory
 // once per launch and every inner iteration streams it from there (no L2/HBM traffic inside the loop).
@@ -256,6 +292,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               int4 sd = s_seg[s - cs];
               int seg_end = s_seg[s - cs + 1].x;
               float Fm[9], g[16];
+              float2 g2[12];  // non-eval kernel: the accumulators live here (x = scalar path and row A, y = row B)
               int nval = 0;
               auto begin_segment = [&]() {
                 float mine = 0.f;
@@ -264,11 +301,22 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Fm[k] = __shfl_sync(0xffffffffu, mine, k);
                 if (kEval && pr.dbg_F && lane < 9) pr.dbg_F[(size_t)s * 9 + lane] = mine;
+                if (kEval) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) g[k] = 0.f;
+                  for (int k = 0; k < 16; ++k) g[k] = 0.f;
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 12; ++k) g2[k] = make_float2(0.f, 0.f);
+                }
                 nval = 0;
               };
               auto end_segment = [&]() {
+                if (!kEval) {
+#pragma unroll
+                  for (int k = 0; k < 12; ++k) g[k] = g2[k].x + g2[k].y;
+#pragma unroll
+                  for (int k = 12; k < 16; ++k) g[k] = 0.f;
+                }
                 nval = __reduce_add_sync(0xffffffffu, (int)g[11]);  // per-lane counts are exact small integers
                 const float tot = warp_reduce16(g, lane);
                 const int slot = warp_reduce16_slot(lane);
@@ -287,8 +335,13 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
                   float4 pt[kGgsUnroll];
 #pragma unroll
                   for (int u = 0; u < kGgsUnroll; ++u) pt[u] = ring_ptr[(st * kGgsUnroll + u) * 32 + lane];
+                  if (kEval) {
 #pragma unroll
-                  for (int u = 0; u < kGgsUnroll; ++u) sampson_match<kEval>(pt[u], Fm, true, P.smax, g);
+                    for (int u = 0; u < kGgsUnroll; ++u) sampson_match<kEval>(pt[u], Fm, true, P.smax, g);
+                  } else {
+#pragma unroll
+                    for (int u = 0; u < kGgsUnroll; u += 2) sampson_match2(pt[u], pt[u + 1], Fm, P.smax, g2);
+                  }
                 } else {
 #pragma unroll
                   for (int u = 0; u < kGgsUnroll; ++u) {
@@ -303,7 +356,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
                       }
                       const float4 pt = ring_ptr[(st * kGgsUnroll + u) * 32 + lane];
                       const bool inb = (q - sd.x) * 32 + lane < sd.y;
-                      sampson_match<kEval>(pt, Fm, inb, P.smax, g);
+                      if (kEval) sampson_match<kEval>(pt, Fm, inb, P.smax, g);
+                      else sampson_match<false, 2>(pt, Fm, inb, P.smax, reinterpret_cast<float*>(g2));
                     }
                   }
                 }
@@ -338,11 +392,26 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               const int nr = r_end - r;
               // rounds without padding rows (all but possibly the segment's last one) run a select-free body
               const int n_full = max(0, min(nr, seg_first + seg_count / 32 - r));
+              if (kEval) {
 #pragma unroll 4
-              for (int q = 0; q < n_full; ++q) sampson_match<kEval>(base[q * 32], Fm, true, P.smax, g);
-              for (int q = n_full; q < nr; ++q) {
-                const bool inb = (r + q - seg_first) * 32 + lane < seg_count;
-                sampson_match<kEval>(base[q * 32], Fm, inb, P.smax, g);
+                for (int q = 0; q < n_full; ++q) sampson_match<kEval>(base[q * 32], Fm, true, P.smax, g);
+                for (int q = n_full; q < nr; ++q) {
+                  const bool inb = (r + q - seg_first) * 32 + lane < seg_count;
+                  sampson_match<kEval>(base[q * 32], Fm, inb, P.smax, g);
+                }
+              } else {  // packed fp32x2 body, two rounds per step; the accumulators live in g2 (x: row A / scalar tail, y: row B)
+                float2 g2[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) g2[k] = make_float2(0.f, 0.f);
+                int qd = 0;
+#pragma unroll 2
+                for (; qd + 1 < n_full; qd += 2) sampson_match2(base[qd * 32], base[(qd + 1) * 32], Fm, P.smax, g2);
+                for (int q = qd; q < nr; ++q) {
+                  const bool inb = (r + q - seg_first) * 32 + lane < seg_count;
+                  sampson_match<false, 2>(base[q * 32], Fm, inb, P.smax, reinterpret_cast<float*>(g2));
+                }
+#pragma unroll
+                for (int k = 0; k < 12; ++k) g[k] = g2[k].x + g2[k].y;
               }
             } else {
               // software-pipelined stream: the next batch of kGgsUnroll rounds (2 KB per warp) is requested before the
