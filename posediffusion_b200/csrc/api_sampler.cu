@@ -203,6 +203,8 @@ void pdb_destroy(pdb_context* c) {
   if (ctx->ggs_ws) cudaFree(ctx->ggs_ws);
   if (ctx->den_ws) cudaFree(ctx->den_ws);
   if (ctx->stage) cudaFree(ctx->stage);
+  if (ctx->tc_graph) cudaGraphExecDestroy(ctx->tc_graph);
+  if (ctx->tc_capture_stream) cudaStreamDestroy(ctx->tc_capture_stream);
   for (auto& b : ctx->pool) cudaFree(b.first);
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->ggs_clock) cudaFree(ctx->ggs_clock);

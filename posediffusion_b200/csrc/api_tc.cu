@@ -143,10 +143,14 @@ __global__ void __launch_bounds__(kDenThreads) attention_kernel(const float* __r
   const int item = blockIdx.x;
   attention_item(att_smem, qkv, att, item / (kHeads * chunks), (item / chunks) % kHeads, item % chunks, frames);
 }
-__global__ void __launch_bounds__(kDenThreads) tail_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R, int t, int last) {
+// the timestep lives on the device (tstate = {t, t_lo}) so that one captured graph serves every diffusion step
+__global__ void __launch_bounds__(kDenThreads) tail_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R, const int* __restrict__ tstate) {
   const int s = blockIdx.x * kDenWarps + (threadIdx.x >> 5);
-  if (s < R.tokens) tail_token(W, R, s, t, last != 0);
+  const int t = tstate[0];
+  if (s < R.tokens) tail_token(W, R, s, t, t == tstate[1]);
 }
+__global__ void step_set_kernel(int* tstate, int t, int t_lo) { tstate[0] = t; tstate[1] = t_lo; }
+__global__ void step_dec_kernel(int* tstate) { tstate[0] -= 1; }
 
 }  // namespace
 
@@ -158,6 +162,7 @@ int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
   const int S = run.tokens, B = run.batch, N = run.frames;
   const size_t need = sizeof(float) * (denoiser_ws_floats(S) + (size_t)S * (kPoseEmbPad + 2) + 64);
   if (int rc = ensure_buffer(ctx, &ctx->den_ws, &ctx->den_ws_bytes, need)) return rc;
+  int* tstate = reinterpret_cast<int*>(ctx->den_ws) + 32;  // words 32..33 of the 256-byte header (0 = barrier counter)
   float* ws = static_cast<float*>(ctx->den_ws) + 64;
   run.zproj = ws; ws += (size_t)S * kDM;
   run.h = ws;     ws += (size_t)S * kDM;
@@ -168,13 +173,13 @@ int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
   float* emb = ws; ws += (size_t)S * kPoseEmbPad;
   float* mean = ws; ws += S;
   float* rstd = ws;
-  auto lin = [&](const float* X, const float* Wm, int O, int K, const float* bias, const float* residual, int ldr,
-                 const float* colsum, float* Y, int relu) {
+  auto lin = [&](const float* X, const float* Wm, int O, int K, const float* bias, const int* t_ptr, const float* residual, int ldr,
+                 const float* colsum, float* Y, int relu, cudaStream_t s) {
     TcEpilogue E = {};
-    E.bias = bias; E.residual = residual; E.ldr = ldr;
+    E.bias = bias; E.t_ptr = t_ptr; E.bias_t_stride = kDM; E.residual = residual; E.ldr = ldr;
     E.colsum = colsum; E.row_mean = colsum ? mean : nullptr; E.row_rstd = colsum ? rstd : nullptr;
     E.Y = Y; E.ldy = O; E.S = S; E.O = O; E.K = K; E.relu = relu;
-    return enqueue_tc_linear(ctx, X, Wm, E, st);
+    return enqueue_tc_linear(ctx, X, Wm, E, s);
   };
   const size_t att_smem = sizeof(float) * ((size_t)N * (kHD + 4) + (size_t)N * kHD + 2 * kDenWarps * kHD) + 64;
   static size_t att_attr = 0;
@@ -183,29 +188,71 @@ int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
     att_attr = att_smem;
   }
   const int chunks = (N + kDenWarps - 1) / kDenWarps;
+  const bool was_profiling = ctx->profiling;
+  ScopedTimer total(ctx, st, 1);  // one event pair around the whole call (events cannot be recorded inside the capture)
+  ctx->profiling = false;
   if (run.compute_zproj) {
-    if (int rc = lin(run.z, T.wz, kDM, kZ, T.b_first, nullptr, 0, nullptr, run.zproj, 0)) return rc;
+    if (int rc = lin(run.z, T.wz, kDM, kZ, T.b_first, nullptr, nullptr, 0, nullptr, run.zproj, 0, st)) { ctx->profiling = was_profiling; return rc; }
     pivot_add_kernel<<<(B * kDM + 255) / 256, 256, 0, st>>>(run.zproj, T.w_pivot, B, N);
     ctx->launches += 1;
   }
-  for (int t = run.t_hi; t >= run.t_lo; --t) {
-    embed_kernel<<<(S * kPoseEmbPad + 255) / 256, 256, 0, st>>>(run.x, emb, S);
-    if (int rc = lin(emb, T.wx, kDM, kPoseEmbPad, T.tproj + (size_t)t * kDM, run.zproj, kDM, nullptr, run.h, 0)) return rc;
+  // ---- one diffusion step = 60 launches; captured once per buffer set, replayed per step ----
+  auto enqueue_step = [&](cudaStream_t s) -> int {
+    embed_kernel<<<(S * kPoseEmbPad + 255) / 256, 256, 0, s>>>(run.x, emb, S);
+    if (int rc = lin(emb, T.wx, kDM, kPoseEmbPad, T.tproj, tstate, run.zproj, kDM, nullptr, run.h, 0, s)) return rc;
     for (int l = 0; l < kLayers; ++l) {
       const TcLayer& L = T.layer[l];
-      row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(run.h, mean, rstd, S);
-      if (int rc = lin(run.h, L.wqkv, 3 * kDM, kDM, L.bias_qkv, nullptr, 0, L.colsum_qkv, run.qkv, 0)) return rc;
-      attention_kernel<<<B * kHeads * chunks, kDenThreads, att_smem, st>>>(run.qkv, run.att, N);
-      if (int rc = lin(run.att, L.wout, kDM, kDM, L.bout, run.h, kDM, nullptr, run.h, 0)) return rc;
-      row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(run.h, mean, rstd, S);
-      if (int rc = lin(run.h, L.wff1, kFF, kDM, L.bias_ff1, nullptr, 0, L.colsum_ff1, run.ff, 1)) return rc;
-      if (int rc = lin(run.ff, L.wff2, kDM, kFF, L.bff2, run.h, kDM, nullptr, run.h, 0)) return rc;
-      ctx->launches += 3;
+      row_stats_kernel<<<(S + 7) / 8, 256, 0, s>>>(run.h, mean, rstd, S);
+      if (int rc = lin(run.h, L.wqkv, 3 * kDM, kDM, L.bias_qkv, nullptr, nullptr, 0, L.colsum_qkv, run.qkv, 0, s)) return rc;
+      attention_kernel<<<B * kHeads * chunks, kDenThreads, att_smem, s>>>(run.qkv, run.att, N);
+      if (int rc = lin(run.att, L.wout, kDM, kDM, L.bout, nullptr, run.h, kDM, nullptr, run.h, 0, s)) return rc;
+      row_stats_kernel<<<(S + 7) / 8, 256, 0, s>>>(run.h, mean, rstd, S);
+      if (int rc = lin(run.h, L.wff1, kFF, kDM, L.bias_ff1, nullptr, nullptr, 0, L.colsum_ff1, run.ff, 1, s)) return rc;
+      if (int rc = lin(run.ff, L.wff2, kDM, kFF, L.bff2, nullptr, run.h, kDM, nullptr, run.h, 0, s)) return rc;
     }
-    if (int rc = lin(run.h, T.wlast0, kHid, kDM, T.blast0, nullptr, 0, nullptr, run.u, 0)) return rc;
-    tail_kernel<<<(S + kDenWarps - 1) / kDenWarps, kDenThreads, 0, st>>>(w->dev, run, t, t == run.t_lo);
-    ctx->launches += 2;
+    if (int rc = lin(run.h, T.wlast0, kHid, kDM, T.blast0, nullptr, nullptr, 0, nullptr, run.u, 0, s)) return rc;
+    tail_kernel<<<(S + kDenWarps - 1) / kDenWarps, kDenThreads, 0, s>>>(w->dev, run, tstate);
+    step_dec_kernel<<<1, 1, 0, s>>>(tstate);
+    return PDB_OK;
+  };
+  constexpr int kNodes = 2 + kLayers * 7 + 3;
+  std::vector<size_t> key = {(size_t)S, (size_t)B, (size_t)N, (size_t)run.guide_below, (size_t)ctx->den_ws, (size_t)run.x,
+                             (size_t)run.draws, (size_t)run.trail, (size_t)run.eps_out, (size_t)run.x0_out, (size_t)run.mean_out,
+                             (size_t)w->tc_arena};
+  if (!ctx->tc_graph || ctx->tc_graph_key != key) {
+    if (ctx->tc_graph) { cudaGraphExecDestroy(ctx->tc_graph); ctx->tc_graph = nullptr; }
+    if (!ctx->tc_capture_stream) PDB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->tc_capture_stream, cudaStreamNonBlocking));
+    const long long before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    PDB_CUDA(ctx, cudaStreamBeginCapture(ctx->tc_capture_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_step(ctx->tc_capture_stream);
+    cudaError_t err = cudaStreamEndCapture(ctx->tc_capture_stream, &graph);
+    ctx->launches = before;  // nothing ran yet
+    if (rc != PDB_OK || err != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      ctx->profiling = was_profiling;
+      return rc != PDB_OK ? rc : ctx->fail(PDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
+    }
+    err = cudaGraphInstantiate(&ctx->tc_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) {
+      ctx->tc_graph = nullptr;
+      ctx->profiling = was_profiling;
+      return ctx->fail(PDB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(err));
+    }
+    ctx->tc_graph_key = key;
+    ctx->tc_graph_nodes = kNodes;
   }
+  step_set_kernel<<<1, 1, 0, st>>>(tstate, run.t_hi, run.t_lo);
+  for (int t = run.t_hi; t >= run.t_lo; --t) {
+    cudaError_t err = cudaGraphLaunch(ctx->tc_graph, st);
+    if (err != cudaSuccess) {
+      ctx->profiling = was_profiling;
+      return ctx->fail(PDB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(err));
+    }
+  }
+  ctx->launches += 1 + (long long)kNodes * (run.t_hi - run.t_lo + 1);
+  ctx->profiling = was_profiling;
   PDB_CUDA(ctx, cudaGetLastError());
   return PDB_OK;
 }

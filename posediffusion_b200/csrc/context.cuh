@@ -30,6 +30,11 @@ struct Context {
   // stage timing probe of the GGS kernel (debug): [ctas][8] cycle sums
   long long* ggs_clock = nullptr;
   int ggs_clock_ctas = 0;
+  // tensor-core engine: one captured CUDA graph of a whole diffusion step, replayed once per step (t lives on the device)
+  cudaGraphExec_t tc_graph = nullptr;
+  std::vector<size_t> tc_graph_key;
+  cudaStream_t tc_capture_stream = nullptr;
+  int tc_graph_nodes = 0;
   int denoiser_engine = 0;  // 0 auto, 1 fp32 persistent kernel, 2 tcgen05/TMA tiles (TF32)
   // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser
   bool profiling = false;

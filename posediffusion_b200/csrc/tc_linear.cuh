@@ -22,6 +22,8 @@ constexpr int kTcBK = 32;   // floats per stage (128 bytes = one swizzle atom), 
 
 struct TcEpilogue {
   const float* bias;      // [O] or null
+  const int* t_ptr;       // optional: device-side timestep; the bias row used is bias + (*t_ptr) * bias_t_stride
+  int bias_t_stride;
   const float* residual;  // [S, ldr] or null (may alias Y: each element is read then written by the same thread)
   int ldr;
   const float* row_mean;  // folded LayerNorm: Y = rstd_s * (acc - mean_s * colsum_o) + bias_o   (all three or none)
@@ -154,6 +156,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = m0 + quarter * 32 + lane;
     const bool row_ok = row < E.S;
+    const float* bias = E.bias;
+    if (bias && E.t_ptr) bias += (size_t)(*E.t_ptr) * E.bias_t_stride;
     float mean = 0.f, rstd = 1.f;
     if (E.colsum && row_ok) {
       mean = E.row_mean[row];
@@ -174,7 +178,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int col = n0 + c0 + j + t;
             float x = v[j + t];
             if (E.colsum) x = rstd * (x - mean * __ldg(E.colsum + col));
-            if (E.bias) x += __ldg(E.bias + col);
+            if (bias) x += __ldg(bias + col);
             o[t] = x;
           }
           if (rrow) {
