@@ -81,20 +81,6 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Grid-wide barrier for a group of co-resident CTAs (cooperative launch).  `counter` only ever grows;
-// the caller passes the arrival count that marks this barrier as complete.
-__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    red_release_add_u32(counter, 1u);
-    while (ld_acquire_u32(counter) < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk asynchronous copy (global -> shared, completion counted in bytes on an mbarrier)
 // ---------------------------------------------------------------------------------------------

@@ -377,6 +377,31 @@ def test_batched_denoiser_equals_singles(sampler, dev):
         np.testing.assert_allclose(full[i].cpu().numpy(), one[0].cpu().numpy(), rtol=0, atol=1e-6)
 
 
+def test_host_buffer_entry_equals_device_entry(sampler, dev):
+    """pdb_sample_loop_host (pinned host buffers, the e2e call) == pdb_sample_loop on device buffers."""
+    ctx = sampler.model.native_context()
+    frames = 6
+    m, _, _ = syn.scene_matches(frames, 48, seed=61)
+    cfg = syn.default_ggs_cfg()
+    cfg.update(iter_num=3, min_matches=0, verbose=False)
+    z = syn.random_features(2, frames, 61)
+    draws = syn.predraw_noise(2, frames, seed=61)
+    packs = [ctx.pack_matches(m), ctx.pack_matches(m)]
+    pose_d, trail_d, stats_d = ctx.sample_loop(z.to(dev), draws.to(dev), packs, cfg, 10)
+    pose_h = np.zeros((2, frames, 9), np.float32)
+    trail_h = np.zeros((101, 2, frames, 9), np.float32)
+    stats_h = np.zeros(10 * 2, dtype=_native.GGS_STATS_DTYPE)
+    ctx.sample_loop_host(z.numpy(), draws.numpy(), packs, cfg, 10, pose_h, trail_h, stats_h)
+    scale = np.abs(trail_h).max()
+    # identical kernels on identical data; only the GGS atomics' ordering may differ between the two runs
+    np.testing.assert_allclose(trail_h[:91], trail_d[:91].cpu().numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(pose_h, pose_d.cpu().numpy(), rtol=0, atol=1e-3 * scale)
+    dev_stats = _native.stats_to_numpy(stats_d)
+    assert np.array_equal(stats_h["iters"], dev_stats["iters"]) and stats_h["iters"].sum() == 10 * 2 * 21
+    # both sequences of the batch saw the same inputs except z / noise
+    assert not np.allclose(pose_h[0], pose_h[1])
+
+
 def test_pose_diffusion_model_api(dev, golden_state):
     model = pdb.PoseDiffusionModel(
         pose_encoding_type="absT_quaR_logFL", IMAGE_FEATURE_EXTRACTOR=None,
