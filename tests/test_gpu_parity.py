@@ -292,6 +292,34 @@ def test_streaming_paths_agree(ctx, dev, mode, monkeypatch):
     np.testing.assert_allclose(p0[0].cpu().numpy(), want[0].numpy(), rtol=0, atol=3e-5 * np.abs(want).max().item())
 
 
+def test_streaming_ring_at_config5_size(ctx, dev):
+    """BASELINE config 5 size (N=80, 6320 ordered pairs x 4096 = 25 886 720 matches, 414 MB): the bulk-async ring streams
+    ~340 rounds per warp.  Size-independent checks: statistics are additive over a split of the pairs, the valid count is
+    reproducible, and the gradient of the union is the count-weighted mean of the parts."""
+    frames, per_pair = 80, 4096
+    m = syn.uniform_matches(frames, per_pair, seed=3)
+    _, _, start = syn.scene_matches(frames, 2, seed=4)
+    pose = torch.from_numpy(start).to(dev)
+    pm = ctx.pack_matches(m)
+    assert (pm.m_total, pm.segments, pm.rounds) == (6320 * 4096, 6320, 6320 * 128)
+    g_all, s_all, _, _ = ctx.sampson_eval(pm, pose)
+    g_again, s_again, _, _ = ctx.sampson_eval(pm, pose)
+    assert s_all[1].item() == s_again[1].item() and s_all[1].item() > 1000
+    half = (6320 // 2) * per_pair
+    parts = []
+    for lo, hi in ((0, half), (half, 6320 * per_pair)):
+        sub = {"kp1": m["kp1"][lo:hi], "kp2": m["kp2"][lo:hi], "i12": m["i12"][lo:hi], "img_shape": m["img_shape"]}
+        g, sc, _, _ = ctx.sampson_eval(ctx.pack_matches(sub), pose)
+        parts.append((g, sc))
+    n1, n2 = parts[0][1][1].item(), parts[1][1][1].item()
+    assert n1 + n2 == s_all[1].item()
+    loss = (parts[0][1][0].item() * n1 + parts[1][1][0].item() * n2) / (n1 + n2)
+    assert abs(loss - s_all[0].item()) <= 2e-4 * abs(s_all[0].item())
+    g_mix = (parts[0][0] * n1 + parts[1][0] * n2) / (n1 + n2)
+    assert (g_mix - g_all).abs().max().item() <= 2e-4 * g_all.abs().max().item()
+    assert (g_all - g_again).abs().max().item() <= 5e-5 * g_all.abs().max().item()
+
+
 def test_matches_pack_validation(ctx):
     m = syn.uniform_matches(4, 8, seed=1)
     bad = dict(m)
