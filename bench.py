@@ -291,6 +291,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "wall_s_timed_region": wall,
+        "published_reference_note": "reference README.md:45 quotes ~60 s of sampling for a 20-frame GGS sequence on a Quadro GP100 (~1.7 steps/s, real hloc matches): other hardware, not this synthetic config, hence vs_baseline = null",
         "kernel_ms_per_loop": {"ggs": ggs_ms / args.steps, "denoiser": den_ms / args.steps, "ggs_launches": ggs_n // args.steps,
                                "denoiser_launches": den_n // args.steps},
     }
