@@ -315,7 +315,7 @@ def main():
                     if args.workload == "cfg3" else
                     "algorithmic bytes = 16 B x matches x inner iterations, streamed from HBM every inner iteration through the TMA unit",
         }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only
         threads = min(os.cpu_count() or 1, 32)
         res = cpu_reference_run(frames, per_pair, args.seed, threads, args.cpu_budget)
         line["cpu_baseline"] = {"value": res["steps_per_s"], "unit": "diffusion steps/s", "cores": res["threads"], "kind": "port",

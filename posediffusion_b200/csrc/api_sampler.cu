@@ -1,5 +1,6 @@
 // C-ABI entry points: denoiser weights, denoiser forward, p_sample, p_sample_loop (device and host buffers).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -178,6 +179,10 @@ int enqueue_denoiser(Context* ctx, DenoiserRun run, cudaStream_t st) {
   const int tiles = (S + TS - 1) / TS;
   int grid = tiles * (3 * kDM / kFPI);  // widest stage (QKV)
   if (grid > ctx->sm_count) grid = ctx->sm_count;
+  if (const char* g = getenv("PDB_DEN_GRID")) {  // tuning knob: number of CTAs of the persistent denoiser kernel
+    const int v = atoi(g);
+    if (v >= 1 && v < grid) grid = v;
+  }
   switch (TS) {
     case 8: return launch_denoiser<8>(ctx, run, grid, st);
     case 16: return launch_denoiser<16>(ctx, run, grid, st);
