@@ -445,3 +445,15 @@ def test_pose_diffusion_model_api(dev, golden_state):
     torch.manual_seed(0)
     again = model(z=z, training=False)["pred_cameras"]
     assert torch.equal(cams.T, again.T)  # deterministic given the seed (GGS off: no atomics on the path)
+
+
+def test_example_demo_runs(capsys):
+    import importlib.util, os
+    from conftest import ROOT
+
+    spec = importlib.util.spec_from_file_location("demo_synthetic", os.path.join(ROOT, "examples", "demo_synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main(frames=6, matches_per_pair=64)
+    out = capsys.readouterr().out
+    assert "GGS off" in out and "GGS on" in out
