@@ -12,6 +12,7 @@
  *   pdb_p_sample           <- GaussianDiffusion.p_sample                 (models/gaussian_diffuser.py:249-282)
  *   pdb_matches_pack       <- matches_dict -> device tensors, pair_idx   (util/geometry_guided_sampling.py:16-45,
  *                                                                          util/match_extraction.py:50-77 output format)
+ *   pdb_matches_pack_colmap<- colmap_keypoint_to_pytorch3d fused into the packer (util/match_extraction.py:50-77)
  *   pdb_sampson_eval       <- compute_sampson_distance + backward        (util/geometry_guided_sampling.py:129-172)
  *   pdb_ggs                <- geometry_guided_sampling (5 x GGS_optimize) (util/geometry_guided_sampling.py:14-126)
  *   pdb_sample_loop        <- GaussianDiffusion.sample / p_sample_loop   (models/gaussian_diffuser.py:285-306)
@@ -136,6 +137,14 @@ int pdb_p_sample(pdb_context* ctx, const float* x_dev, int32_t t, const float* z
 int pdb_matches_pack(pdb_context* ctx, const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total,
                      int32_t frames, int32_t height, int32_t width, int32_t on_device, void* stream,
                      pdb_matches** out);
+/* The same ingestion from the COLMAP / hloc tables, fusing the reference's remap (util/match_extraction.py:50-77):
+ * keypoints[i] = [kp_counts[i], 2] COLMAP pixel coordinates of image i (float32 or float64, `kp_is_f64`),
+ * pair_ids[p] = (r, q) 1-based image ids, pair_matches[p] = [match_counts[p], 2] keypoint index pairs (NULL or count 0 = no
+ * matches), bboxes_xyxy [n_images, 4] and scales [n_images] from load_and_preprocess_images.  kp' = (kp - 0.5 - bbox_xy) * scale. */
+int pdb_matches_pack_colmap(pdb_context* ctx, int32_t n_images, const void* const* keypoints, const int32_t* kp_counts,
+                            int32_t kp_is_f64, int32_t n_pairs, const int32_t* pair_ids, const int32_t* const* pair_matches,
+                            const int32_t* match_counts, const double* bboxes_xyxy, const double* scales, int32_t frames,
+                            int32_t height, int32_t width, void* stream, pdb_matches** out);
 void pdb_matches_free(pdb_matches* m);
 int pdb_matches_info(const pdb_matches* m, int64_t* m_total, int32_t* segments, int64_t* rounds, int32_t* frames);
 

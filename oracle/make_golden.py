@@ -211,6 +211,40 @@ def golden_loop(ref, sampler):
     np.savez(os.path.join(OUT, "loop.npz"), **out)
 
 
+def synthetic_colmap_tables(frames=5, seed=51):
+    """COLMAP-format inputs of colmap_keypoint_to_pytorch3d: float32 keypoints per (1-based) image, raw index matches per
+    unordered pair (one pair without matches), crop boxes / scales as load_and_preprocess_images builds them."""
+    rng = np.random.default_rng(seed)
+    keypoints = {i + 1: rng.uniform(0, 1000, size=(int(rng.integers(40, 90)), 2)).astype(np.float32) for i in range(frames)}
+    matches = {}
+    for a in range(1, frames + 1):
+        for b in range(a + 1, frames + 1):
+            if (a, b) == (2, 4):
+                matches[(a, b)] = None
+                continue
+            m = int(rng.integers(5, 60))
+            matches[(a, b)] = np.stack([rng.integers(0, len(keypoints[a]), m), rng.integers(0, len(keypoints[b]), m)], 1).astype(np.int64)
+    bboxes = np.stack([np.array([rng.integers(0, 300), rng.integers(0, 40), 0, 0], dtype=np.float32) for _ in range(frames)])
+    bboxes[:, 2:] = bboxes[:, :2] + 1066
+    image_info = {"size": (1066, 1066), "bboxes_xyxy": bboxes, "resized_scales": np.stack([224 / 1066] * frames)}
+    return matches, keypoints, image_info
+
+
+def golden_colmap():
+    """Runs the reference's OWN colmap_keypoint_to_pytorch3d.  util/match_extraction.py imports hloc / pycolmap (absent) at
+    module level, so the function's source is extracted from the file with `ast` and executed as is."""
+    import ast
+
+    path = os.path.join(os.environ.get("POSEDIFF_REFERENCE_ROOT", "/root/reference"), "pose_diffusion", "util", "match_extraction.py")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "colmap_keypoint_to_pytorch3d")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    matches, keypoints, image_info = synthetic_colmap_tables()
+    kp1, kp2, i12 = ns["colmap_keypoint_to_pytorch3d"](matches, {k: v.copy() for k, v in keypoints.items()}, image_info)
+    np.savez(os.path.join(OUT, "colmap.npz"), kp1=kp1, kp2=kp2, i12=i12, numpy_version=np.__version__)
+
+
 def main():
     torch.set_num_threads(1)  # bit-stable fixtures
     os.makedirs(OUT, exist_ok=True)
@@ -223,6 +257,7 @@ def main():
     golden_sampson(ref)
     golden_ggs(ref)
     golden_loop(ref, sampler)
+    golden_colmap()
     for name in sorted(os.listdir(OUT)):
         print(name, os.path.getsize(os.path.join(OUT, name)))
 

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <thread>
 
@@ -137,58 +138,17 @@ int pdb_debug_ggs_clocks(pdb_context* c, int32_t enable, int64_t* out, int32_t m
 
 int64_t pdb_launch_count(const pdb_context* c) { return c ? reinterpret_cast<const Context*>(c)->launches : 0; }
 
-// ------------------------------------------------------------------------------------------------
-// correspondences
-// ------------------------------------------------------------------------------------------------
-int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total,
-                     int32_t frames, int32_t height, int32_t width, int32_t on_device, void* stream,
-                     pdb_matches** out) {
-  if (!c || !out) return PDB_ERR_INVALID;
-  Context* ctx = reinterpret_cast<Context*>(c);
-  *out = nullptr;
-  if (m_total < 0 || frames < 1 || height < 1 || width < 1) return ctx->fail(PDB_ERR_INVALID, "bad match set shape");
-  if (frames > PDB_MAX_FRAMES) return ctx->fail(PDB_ERR_LIMIT, "frames %d > PDB_MAX_FRAMES %d", frames, PDB_MAX_FRAMES);
-  if (m_total > 0 && (!kp1 || !kp2 || !i12)) return ctx->fail(PDB_ERR_INVALID, "null match arrays");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+}  // extern "C"
 
-  std::vector<double> h1, h2;
-  std::vector<int64_t> hi;
-  if (on_device && m_total > 0) {  // bring reference-format device arrays to the host packer
-    h1.resize(2 * m_total);
-    h2.resize(2 * m_total);
-    hi.resize(2 * m_total);
-    PDB_CUDA(ctx, cudaMemcpyAsync(h1.data(), kp1, sizeof(double) * 2 * m_total, cudaMemcpyDeviceToHost, st));
-    PDB_CUDA(ctx, cudaMemcpyAsync(h2.data(), kp2, sizeof(double) * 2 * m_total, cudaMemcpyDeviceToHost, st));
-    PDB_CUDA(ctx, cudaMemcpyAsync(hi.data(), i12, sizeof(int64_t) * 2 * m_total, cudaMemcpyDeviceToHost, st));
-    PDB_CUDA(ctx, cudaStreamSynchronize(st));
-    kp1 = h1.data();
-    kp2 = h2.data();
-    i12 = hi.data();
-  }
-  // pass 1: maximal runs of equal (a, b) -> segments; pair index a*N+b as the reference (:26) computes it
-  std::vector<int4> segs;
-  long long rounds = 0;
-  for (int64_t i = 0; i < m_total;) {
-    const int64_t a = i12[2 * i], b = i12[2 * i + 1];
-    if (a < 0 || a >= frames || b < 0 || b >= frames)
-      return ctx->fail(PDB_ERR_INVALID, "i12[%lld] = (%lld, %lld) outside [0, %d)", (long long)i, (long long)a, (long long)b, frames);
-    int64_t j = i + 1;
-    while (j < m_total && i12[2 * j] == a && i12[2 * j + 1] == b) ++j;
-    int64_t remaining = j - i, start = i;
-    while (remaining > 0) {  // keep per-segment counts inside int32
-      const int64_t take = remaining > (1 << 30) ? (1 << 30) : remaining;
-      segs.push_back(make_int4((int)rounds, (int)take, (int)a, (int)b));
-      rounds += (take + 31) / 32;
-      remaining -= take;
-      start += take;
-    }
-    i = j;
-  }
+namespace {
+// Common tail of the packers: `segs` (without sentinel) are laid out in rounds, `row(src)` yields the fp32 quad of the
+// src-th match in segment order.  Fills pinned staging memory (threaded for big inputs), uploads, returns the handle.
+template <typename Row>
+int finish_pack(Context* ctx, std::vector<int4>& segs, long long rounds, int64_t m_total, int frames, int height, int width,
+                cudaStream_t st, pdb_matches** out, Row row) {
   if (rounds > 0x7fffffffLL / 32) return ctx->fail(PDB_ERR_LIMIT, "too many matches");
   const int nseg = (int)segs.size();
   segs.push_back(make_int4((int)rounds, 0, 0, 0));
-  // pass 2: fp32 quads, padded to 32-row rounds per segment, written straight into pinned staging memory
   const size_t pts_bytes = sizeof(float4) * ((size_t)rounds * 32 ? (size_t)rounds * 32 : 1);
   const size_t segs_bytes = sizeof(int4) * segs.size();
   const size_t stage_need = pts_bytes + segs_bytes;
@@ -210,10 +170,7 @@ int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const
         float4* dst = hpts + (size_t)segs[s].x * 32;
         const int64_t src0 = first[s];
         const int cnt = segs[s].y, padded = (cnt + 31) / 32 * 32;
-        for (int k = 0; k < cnt; ++k) {
-          const int64_t src = src0 + k;
-          dst[k] = make_float4((float)kp1[2 * src], (float)kp1[2 * src + 1], (float)kp2[2 * src], (float)kp2[2 * src + 1]);
-        }
+        for (int k = 0; k < cnt; ++k) dst[k] = row(src0 + k);
         for (int k = cnt; k < padded; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
@@ -263,6 +220,116 @@ int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const
   }
   *out = reinterpret_cast<pdb_matches*>(m);
   return PDB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------
+// correspondences
+// ------------------------------------------------------------------------------------------------
+int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total,
+                     int32_t frames, int32_t height, int32_t width, int32_t on_device, void* stream,
+                     pdb_matches** out) {
+  if (!c || !out) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  *out = nullptr;
+  if (m_total < 0 || frames < 1 || height < 1 || width < 1) return ctx->fail(PDB_ERR_INVALID, "bad match set shape");
+  if (frames > PDB_MAX_FRAMES) return ctx->fail(PDB_ERR_LIMIT, "frames %d > PDB_MAX_FRAMES %d", frames, PDB_MAX_FRAMES);
+  if (m_total > 0 && (!kp1 || !kp2 || !i12)) return ctx->fail(PDB_ERR_INVALID, "null match arrays");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  std::vector<double> h1, h2;
+  std::vector<int64_t> hi;
+  if (on_device && m_total > 0) {  // bring reference-format device arrays to the host packer
+    h1.resize(2 * m_total);
+    h2.resize(2 * m_total);
+    hi.resize(2 * m_total);
+    PDB_CUDA(ctx, cudaMemcpyAsync(h1.data(), kp1, sizeof(double) * 2 * m_total, cudaMemcpyDeviceToHost, st));
+    PDB_CUDA(ctx, cudaMemcpyAsync(h2.data(), kp2, sizeof(double) * 2 * m_total, cudaMemcpyDeviceToHost, st));
+    PDB_CUDA(ctx, cudaMemcpyAsync(hi.data(), i12, sizeof(int64_t) * 2 * m_total, cudaMemcpyDeviceToHost, st));
+    PDB_CUDA(ctx, cudaStreamSynchronize(st));
+    kp1 = h1.data();
+    kp2 = h2.data();
+    i12 = hi.data();
+  }
+  // pass 1: maximal runs of equal (a, b) -> segments; pair index a*N+b as the reference (:26) computes it
+  std::vector<int4> segs;
+  long long rounds = 0;
+  for (int64_t i = 0; i < m_total;) {
+    const int64_t a = i12[2 * i], b = i12[2 * i + 1];
+    if (a < 0 || a >= frames || b < 0 || b >= frames)
+      return ctx->fail(PDB_ERR_INVALID, "i12[%lld] = (%lld, %lld) outside [0, %d)", (long long)i, (long long)a, (long long)b, frames);
+    int64_t j = i + 1;
+    while (j < m_total && i12[2 * j] == a && i12[2 * j + 1] == b) ++j;
+    int64_t remaining = j - i, start = i;
+    while (remaining > 0) {  // keep per-segment counts inside int32
+      const int64_t take = remaining > (1 << 30) ? (1 << 30) : remaining;
+      segs.push_back(make_int4((int)rounds, (int)take, (int)a, (int)b));
+      rounds += (take + 31) / 32;
+      remaining -= take;
+      start += take;
+    }
+    i = j;
+  }
+  return finish_pack(ctx, segs, rounds, m_total, frames, height, width, st, out, [&](int64_t src) {
+    return make_float4((float)kp1[2 * src], (float)kp1[2 * src + 1], (float)kp2[2 * src], (float)kp2[2 * src + 1]);
+  });
+}
+
+// Match ingestion straight from the COLMAP / hloc tables (util/match_extraction.py:50-77, colmap_keypoint_to_pytorch3d):
+// keypoints per image in COLMAP pixel coordinates, raw match index pairs per image pair, crop boxes and resize scales of
+// load_and_preprocess_images.  The remap  kp' = (kp - 0.5 - bbox_xy[img]) * scale[img]  is applied in float64 (numpy's
+// promotion in the reference) while the rows are gathered, so the 48 B/match kp1 / kp2 / i12 arrays never exist.
+int pdb_matches_pack_colmap(pdb_context* c, int32_t n_images, const void* const* keypoints, const int32_t* kp_counts,
+                            int32_t kp_is_f64, int32_t n_pairs, const int32_t* pair_ids, const int32_t* const* pair_matches,
+                            const int32_t* match_counts, const double* bboxes_xyxy, const double* scales, int32_t frames,
+                            int32_t height, int32_t width, void* stream, pdb_matches** out) {
+  if (!c || !out) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  *out = nullptr;
+  if (n_images < 1 || n_pairs < 0 || frames < 1 || !keypoints || !kp_counts || !bboxes_xyxy || !scales ||
+      (n_pairs > 0 && (!pair_ids || !pair_matches || !match_counts)))
+    return ctx->fail(PDB_ERR_INVALID, "bad COLMAP match tables");
+  if (frames > PDB_MAX_FRAMES) return ctx->fail(PDB_ERR_LIMIT, "frames %d > PDB_MAX_FRAMES %d", frames, PDB_MAX_FRAMES);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int4> segs;
+  std::vector<int> seg_pair;  // pair table row of each segment
+  long long rounds = 0;
+  int64_t m_total = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int r = pair_ids[2 * p], q = pair_ids[2 * p + 1];  // 1-based COLMAP image ids
+    if (r < 1 || r > n_images || q < 1 || q > n_images || r - 1 >= frames || q - 1 >= frames)
+      return ctx->fail(PDB_ERR_INVALID, "pair %d = (%d, %d) outside the image list", p, r, q);
+    const int cnt = match_counts[p];
+    if (cnt <= 0 || !pair_matches[p]) continue;  // "if pair_match is not None" (:65)
+    for (int k = 0; k < cnt; ++k) {
+      const int i1 = pair_matches[p][2 * k], i2 = pair_matches[p][2 * k + 1];
+      if (i1 < 0 || i1 >= kp_counts[r - 1] || i2 < 0 || i2 >= kp_counts[q - 1])
+        return ctx->fail(PDB_ERR_INVALID, "match %d of pair %d indexes a missing keypoint", k, p);
+    }
+    segs.push_back(make_int4((int)rounds, cnt, r - 1, q - 1));  // i12 = (colmap_id - 1) (:69)
+    seg_pair.push_back(p);
+    rounds += (cnt + 31) / 32;
+    m_total += cnt;
+  }
+  std::vector<int64_t> first(segs.size() + 1, 0);
+  for (size_t s2 = 0; s2 < segs.size(); ++s2) first[s2 + 1] = first[s2] + segs[s2].y;
+  auto kp = [&](int img, int idx, int comp) -> double {
+    const double v = kp_is_f64 ? static_cast<const double*>(keypoints[img])[2 * idx + comp]
+                               : (double)(static_cast<const float*>(keypoints[img])[2 * idx + comp] - 0.5f) + 0.5;
+    // float32 tables: the reference subtracts 0.5 in float32 first (numpy keeps the array dtype), then promotes
+    return (v - 0.5 - bboxes_xyxy[4 * img + comp]) * scales[img];
+  };
+  return finish_pack(ctx, segs, rounds, m_total, frames, height, width, st, out, [&](int64_t src) {
+    const int s2 = (int)(std::upper_bound(first.begin(), first.end(), src) - first.begin()) - 1;
+    const int p = seg_pair[s2], k = (int)(src - first[s2]);
+    const int a = segs[s2].z, b = segs[s2].w;
+    const int i1 = pair_matches[p][2 * k], i2 = pair_matches[p][2 * k + 1];
+    return make_float4((float)kp(a, i1, 0), (float)kp(a, i1, 1), (float)kp(b, i2, 0), (float)kp(b, i2, 1));
+  });
 }
 
 void pdb_matches_free(pdb_matches* pm) {

@@ -457,3 +457,29 @@ def test_example_demo_runs(capsys):
     mod.main(frames=6, matches_per_pair=64)
     out = capsys.readouterr().out
     assert "GGS off" in out and "GGS on" in out
+
+
+def test_colmap_ingestion_equals_reference_format_ingestion(ctx, dev):
+    """pdb_matches_pack_colmap (remap fused into the gather) == pdb_matches_pack of the reference function's output."""
+    from oracle.make_golden import synthetic_colmap_tables
+    from posediffusion_b200.match_extraction import pack_colmap_matches
+
+    g = load_golden("colmap.npz")
+    matches, keypoints, image_info = synthetic_colmap_tables()
+    img_shape = (5, 3, 224, 224)
+    ref_dict = {"kp1": g["kp1"], "kp2": g["kp2"], "i12": g["i12"], "img_shape": img_shape}
+    pm_ref = ctx.pack_matches(ref_dict)
+    pm_col = pack_colmap_matches(ctx, matches, keypoints, image_info, img_shape)
+    assert (pm_col.m_total, pm_col.segments, pm_col.rounds) == (pm_ref.m_total, pm_ref.segments, pm_ref.rounds)
+    pose = torch.from_numpy(syn.scene_matches(5, 4, seed=1)[2]).to(dev)
+    for smax in (10.0, 1e9):  # with a huge threshold every match is valid: the sums see every coordinate
+        g1, s1, F1, G1 = ctx.sampson_eval(pm_ref, pose, sampson_max=smax, dump=True)
+        g2, s2, F2, G2 = ctx.sampson_eval(pm_col, pose, sampson_max=smax, dump=True)
+        assert s1[1].item() == s2[1].item()
+        assert torch.equal(F1, F2)
+        scale = G1.abs().max().item()
+        assert (G1 - G2).abs().max().item() <= 1e-4 * scale
+    bad = dict(matches)
+    bad[(1, 2)] = np.array([[0, 10_000]])
+    with pytest.raises(ValueError):
+        pack_colmap_matches(ctx, bad, keypoints, image_info, img_shape)

@@ -172,3 +172,18 @@ def test_device_geometry_on_host_matches_reference(tag, flags, folded):
     # closer to the fp64 truth than the tolerance we grant the reference's own fp32 chain
     c = s64.sampson_closed_form_f64(g[f"{tag}_pose"], m, *map(bool, flags))
     np.testing.assert_allclose(grad[ok], c["grad"][ok], rtol=0, atol=1e-4 * gmax)
+
+
+def test_colmap_remap_mirror_matches_reference_function():
+    """posediffusion_b200.match_extraction.colmap_keypoint_to_pytorch3d vs the reference's own function
+    (util/match_extraction.py:50-77, executed by oracle/make_golden.py)."""
+    from oracle.make_golden import synthetic_colmap_tables
+    from posediffusion_b200.match_extraction import colmap_keypoint_to_pytorch3d
+
+    g = load_golden("colmap.npz")
+    matches, keypoints, image_info = synthetic_colmap_tables()
+    kp1, kp2, i12 = colmap_keypoint_to_pytorch3d(matches, keypoints, image_info)
+    assert np.array_equal(i12, g["i12"])  # pair / frame indexing bit-exact
+    np.testing.assert_allclose(kp1, g["kp1"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(kp2, g["kp2"], rtol=0, atol=1e-4)
+    assert colmap_keypoint_to_pytorch3d({(1, 2): None}, keypoints, image_info) == (None, None, None)
