@@ -483,3 +483,25 @@ def test_colmap_ingestion_equals_reference_format_ingestion(ctx, dev):
     bad[(1, 2)] = np.array([[0, 10_000]])
     with pytest.raises(ValueError):
         pack_colmap_matches(ctx, bad, keypoints, image_info, img_shape)
+
+
+def test_cond_start_step_edges(sampler, dev):
+    """cond_start_step = 0 -> the guidance callable is never used (gaussian_diffuser.py:270: t < 0 is never true);
+    a start step of 3 guides exactly t = 2, 1, 0 and consumes 1 + 97 draws."""
+    frames = 5
+    m, _, _ = syn.scene_matches(frames, 40, seed=71)
+    cfg = syn.default_ggs_cfg()
+    cfg.update(iter_num=2, min_matches=0, verbose=False)
+    cond = partial(pdb.geometry_guided_sampling, matches_dict=m, GGS_cfg=cfg)
+    z = syn.random_features(1, frames, 71).to(dev)
+    draws = syn.predraw_noise(1, frames, seed=71).to(dev)
+    p_off, t_off = sampler.p_sample_loop([1, frames, 9], z, None, 0, draws=draws)
+    p_zero, t_zero = sampler.p_sample_loop([1, frames, 9], z, cond, 0, draws=draws)
+    assert torch.equal(t_off, t_zero)
+    p3, t3 = sampler.p_sample_loop([1, frames, 9], z, cond, 3, draws=draws)
+    assert torch.equal(t3[:98], t_off[:98]) and not torch.equal(t3[98], t_off[98])
+    stats = _native.stats_to_numpy(sampler.last_ggs_stats).reshape(3, 1)
+    assert (stats["iters"] == np.array([4, 2, 2, 2, 4])).all()
+    torch.manual_seed(7)
+    d3 = sampler.draw_noise((1, frames, 9), dev, 3)
+    assert float(d3[98:].abs().sum()) == 0.0 and float(d3[97].abs().sum()) > 0.0
