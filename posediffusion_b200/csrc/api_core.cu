@@ -381,7 +381,7 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   P.resident_rounds = resident ? (int)rounds_per_cta : 0;
   P.ring = resident ? 0 : 1;
   const size_t smem = fixed + (resident ? (size_t)rounds_per_cta * 512 : (size_t)kRingBytes);
-  static size_t attr_bytes = 0;  // per instantiation
+  size_t& attr_bytes = ctx->attr_ggs[kEval ? 1 : 0];
   if (smem > attr_bytes) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;

@@ -128,7 +128,7 @@ template <int TS>
 int launch_denoiser(Context* ctx, const DenoiserRun& run, int grid, cudaStream_t st) {
   const size_t smem = denoiser_smem_bytes(TS, run.frames);
   if (smem > ctx->smem_optin) return ctx->fail(PDB_ERR_LIMIT, "denoiser needs %zu B shared memory", smem);
-  static size_t attr_bytes = 0;  // static shared memory counts against the opt-in limit: ask for what we use
+  size_t& attr_bytes = ctx->attr_den[TS / 8 - 1];  // static shared memory counts against the opt-in limit: ask for what we use
   if (smem > attr_bytes) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(denoiser_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;

@@ -48,7 +48,7 @@ int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E
   if (int rc = make_map(ctx, &mx, X, E.S, E.K, kTcBM)) return rc;
   if (int rc = make_map(ctx, &mw, W, E.O, E.K, BN)) return rc;
   const size_t smem = tc_smem_bytes(BN);
-  static bool attr = false;
+  bool& attr = ctx->attr_tc;
   if (!attr) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
@@ -182,7 +182,7 @@ int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
     return enqueue_tc_linear(ctx, X, Wm, E, s);
   };
   const size_t att_smem = sizeof(float) * ((size_t)N * (kHD + 4) + (size_t)N * kHD + 2 * kDenWarps * kHD) + 64;
-  static size_t att_attr = 0;
+  size_t& att_attr = ctx->attr_att;
   if (att_smem > att_attr) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
     att_attr = att_smem;

@@ -505,3 +505,27 @@ def test_cond_start_step_edges(sampler, dev):
     torch.manual_seed(7)
     d3 = sampler.draw_noise((1, frames, 9), dev, 3)
     assert float(d3[98:].abs().sum()) == 0.0 and float(d3[97].abs().sum()) > 0.0
+
+
+def test_two_devices_in_one_process():
+    """One pdb_context per GPU inside a single process (the normal deployment is one process per GPU)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    m, _, start = syn.scene_matches(6, 50, seed=81)
+    ref = s64.sampson_closed_form_f64(start, m)
+    state = syn.random_denoiser_state(2)
+    for index in (0, 1):
+        d = torch.device("cuda", index)
+        c = _native.Context.get(d)
+        grad, sc, _, _ = c.sampson_eval(c.pack_matches(m), torch.from_numpy(start).to(d))
+        assert int(sc[1].item()) == ref["n_valid"]
+        np.testing.assert_allclose(grad.cpu().numpy(), ref["grad"], rtol=0, atol=3e-4 * np.abs(ref["grad"]).max())
+        den = pdb.Denoiser(TRANSFORMER=TRANSFORMER)
+        den.load_state_dict(state, strict=True)
+        den = den.to(d)
+        eps = den(torch.zeros(1, 6, 9, device=d), torch.zeros(1, dtype=torch.long, device=d), torch.ones(1, 6, 384, device=d))
+        assert torch.isfinite(eps).all()
+        if index == 0:
+            first = eps.cpu()
+        else:
+            assert torch.allclose(first, eps.cpu(), atol=1e-6)
