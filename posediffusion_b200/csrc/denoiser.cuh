@@ -420,10 +420,14 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
     if (item < n_items) linear_prefetch<K>(wreg, Wp, O, (item % groups) * kFPI);
     if (need_barrier) barrier();
     float* red = Xs + TS * K;
+    int staged_tile = -1;  // the activations of a token tile are staged once and reused by this CTA's later items of the stage
     for (; item < n_items; item += G) {
       const int tt = item / groups, fg = item - tt * groups;
       if (item != (int)blockIdx.x) linear_prefetch<K>(wreg, Wp, O, fg * kFPI);
-      load_x(tt);
+      if (tt != staged_tile) {
+        load_x(tt);
+        staged_tile = tt;
+      }
       __syncthreads();
       linear_item<TS, K>(wreg, Xs, red, fg * kFPI, bias, add1, ld1, add2, add_rs, rs, Y, ldy, tt * TS, S, epi);
     }
