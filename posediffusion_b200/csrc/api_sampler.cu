@@ -112,7 +112,7 @@ size_t tensor_floats(int i) {
 }
 
 int pick_token_tile(int tokens) {
-  const int cand[4] = {8, 16, 24, 32};
+  const int cand[5] = {8, 16, 20, 24, 32};  // 20 = the headline sequence length (no padded token rows)
   int best = 32, best_pad = 1 << 30;
   for (int c : cand) {
     const int pad = (tokens + c - 1) / c * c;
@@ -128,7 +128,7 @@ template <int TS>
 int launch_denoiser(Context* ctx, const DenoiserRun& run, int grid, cudaStream_t st) {
   const size_t smem = denoiser_smem_bytes(TS, run.frames);
   if (smem > ctx->smem_optin) return ctx->fail(PDB_ERR_LIMIT, "denoiser needs %zu B shared memory", smem);
-  size_t& attr_bytes = ctx->attr_den[TS / 8 - 1];  // static shared memory counts against the opt-in limit: ask for what we use
+  size_t& attr_bytes = ctx->attr_den[TS / 4 - 1];  // static shared memory counts against the opt-in limit: ask for what we use
   if (smem > attr_bytes) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(denoiser_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
@@ -186,6 +186,7 @@ int enqueue_denoiser(Context* ctx, DenoiserRun run, cudaStream_t st) {
   switch (TS) {
     case 8: return launch_denoiser<8>(ctx, run, grid, st);
     case 16: return launch_denoiser<16>(ctx, run, grid, st);
+    case 20: return launch_denoiser<20>(ctx, run, grid, st);
     case 24: return launch_denoiser<24>(ctx, run, grid, st);
     default: return launch_denoiser<32>(ctx, run, grid, st);
   }

@@ -36,7 +36,7 @@ struct Context {
   cudaStream_t tc_capture_stream = nullptr;
   int tc_graph_nodes = 0;
   // cudaFuncSetAttribute is per device: remember per context (= per device) what was already requested
-  size_t attr_ggs[2] = {0, 0}, attr_den[4] = {0, 0, 0, 0}, attr_att = 0;
+  size_t attr_ggs[2] = {0, 0}, attr_den[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
   bool attr_tc = false;
   int denoiser_engine = 0;  // 0 auto, 1 fp32 persistent kernel, 2 tcgen05/TMA tiles (TF32)
   // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser

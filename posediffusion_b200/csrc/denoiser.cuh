@@ -203,7 +203,7 @@ __device__ __forceinline__ void linear_item(const LinW<K>& W, const float* __res
                                             const float* __restrict__ add2, const float* __restrict__ add_row_scaled,
                                             const float* __restrict__ row_scale, float* __restrict__ Y, int ldy, int row0,
                                             int valid_end, int epi) {
-  static_assert(TS % 8 == 0, "token tile");
+  static_assert(TS % 4 == 0 && TS <= 32, "token tile");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int PER = LinW<K>::PER;
   const int ks = lane >> 3, f = lane & 7;
