@@ -177,6 +177,34 @@ int pdb_sample_loop_host(pdb_context* ctx, const float* z_host, const float* dra
                          int32_t cond_start_step, float* pose_host, float* trail_host, pdb_ggs_stats* stats_host,
                          void* stream);
 
+/* ---- image features (widened row) ---------------------------------------------------
+ * z = MultiScaleImageFeatureExtractor(image) (models/image_feature_extractor.py:27-87): the DINO ViT-S/16 backbone that the
+ * reference pulls from torch.hub ("facebookresearch/dino:main", dino_vits16 -- third-party, restated in oracle/dino_vit.py),
+ * applied to the ResNet-normalised image at each scale factor (bilinear resize, align_corners=False), class-token features
+ * averaged over the scales (:74-83).  Projections run as tcgen05/TMA tiles with TF32 products (fp32 accumulate).
+ *
+ * `tensors[i]` (fp32, contiguous) in the hub checkpoint's state_dict order (`image_feature_extractor._net.*`): cls_token,
+ * pos_embed[1,197,384], patch_embed.proj.{weight[384,3,16,16],bias}, then for block 0..11: norm1.{weight,bias},
+ * attn.qkv.{weight[1152,384],bias}, attn.proj.{weight,bias}, norm2.{weight,bias}, mlp.fc1.{weight[1536,384],bias},
+ * mlp.fc2.{weight[384,1536],bias}; then norm.{weight,bias}.  numels[i] is checked against that layout. */
+#define PDB_VIT_NUM_TENSORS 150
+int pdb_vit_load(pdb_context* ctx, const float* const* tensors, const int64_t* numels, int32_t count, int32_t on_device,
+                 void* stream);
+/* interpolate_pos_encoding of the hub model for a grid_h x grid_w patch grid: bicubic resampling of the 14x14 table with the
+ * scale factor (grid + 0.1) / 14 (torch F.interpolate semantics, align_corners=False).  HOST-ONLY helper, needs no GPU:
+ * pos_embed_host [197,384] -> out_host [1 + grid_h*grid_w, 384]. */
+int pdb_vit_pos_table(const float* pos_embed_host, int32_t grid_h, int32_t grid_w, float* out_host);
+/* images_dev [n,3,H,W] in [0,1] (what load_and_preprocess_images / the dataloader produce) -> z_dev [n,384].
+ * scale_factors as in cfgs/default.yaml (1, 1/2, 1/3); empty -> PDB_ERR_INVALID (the reference raises ValueError, :75-76).
+ * tokens_debug_dev (may be NULL): receives the residual stream [sum over scales of n*(1+gh*gw), 384] (scale-major, image, token)
+ * after stage `debug_stage` (0 = prepare_tokens, k = block k) -- the parity tests' probe. */
+int pdb_extract_features(pdb_context* ctx, const float* images_dev, int32_t n_images, int32_t height, int32_t width,
+                         const double* scale_factors, int32_t n_scales, float* z_dev, float* tokens_debug_dev,
+                         int32_t debug_stage, void* stream);
+/* The same with host buffers: copies the images in, z out, synchronises the stream. */
+int pdb_extract_features_host(pdb_context* ctx, const float* images_host, int32_t n_images, int32_t height, int32_t width,
+                              const double* scale_factors, int32_t n_scales, float* z_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,9 +9,10 @@ from .camera_transform import PerspectiveCameras, pose_encoding_to_camera
 from .denoiser import Denoiser, TransformerEncoderWrapper
 from .gaussian_diffuser import GaussianDiffusion
 from .geometry_guided_sampling import geometry_guided_sampling
+from .image_feature_extractor import MultiScaleImageFeatureExtractor
 from .pose_diffusion_model import PoseDiffusionModel
 
 __all__ = [
-    "PoseDiffusionModel", "GaussianDiffusion", "Denoiser", "TransformerEncoderWrapper",
+    "PoseDiffusionModel", "GaussianDiffusion", "Denoiser", "TransformerEncoderWrapper", "MultiScaleImageFeatureExtractor",
     "geometry_guided_sampling", "pose_encoding_to_camera", "PerspectiveCameras",
 ]

@@ -22,6 +22,8 @@ NUM_TIMESTEPS = 100
 TARGET_DIM = 9
 Z_DIM = 384
 MAX_FRAMES = 128
+PDB_VIT_NUM_TENSORS = 150
+VIT_DIM = 384
 
 
 class NativeError(RuntimeError):
@@ -79,6 +81,10 @@ EXPORTS = {
     "pdb_sampson_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_ggs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(GgsConfig), C.c_void_p, C.c_void_p]),
     "pdb_sample_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_vit_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_void_p]),
+    "pdb_vit_pos_table": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "pdb_extract_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdb_extract_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p]),
     "pdb_sample_loop_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -111,6 +117,16 @@ def schedule_table(beta_1: float = 1e-4, beta_T: float = 0.1) -> np.ndarray:
     rc = load_library().pdb_schedule_table(out.ctypes.data_as(C.c_void_p), beta_1, beta_T)
     if rc != 0:
         raise NativeError(f"pdb_schedule_table failed ({rc})")
+    return out
+
+
+def vit_pos_table(pos_embed: np.ndarray, grid_h: int, grid_w: int) -> np.ndarray:
+    """interpolate_pos_encoding of the DINO backbone for a grid_h x grid_w patch grid (host helper, no GPU needed)."""
+    pos = np.ascontiguousarray(pos_embed, dtype=np.float32).reshape(197, VIT_DIM)
+    out = np.zeros((1 + grid_h * grid_w, VIT_DIM), dtype=np.float32)
+    rc = load_library().pdb_vit_pos_table(pos.ctypes.data_as(C.c_void_p), grid_h, grid_w, out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise NativeError(f"pdb_vit_pos_table failed ({rc})")
     return out
 
 
@@ -236,6 +252,51 @@ class Context:
         arr = (C.c_void_p * len(keep))(*[C.c_void_p(t.data_ptr()) for t in keep])
         with torch.cuda.device(self.device):
             self._ok(self.lib.pdb_denoiser_load(self.handle, arr, len(keep), _stream_ptr(self.device)), "pdb_denoiser_load")
+
+    def load_vit(self, tensors: Sequence[torch.Tensor]):
+        """DINO ViT-S/16 parameters in hub state_dict order (150 tensors, host or this device)."""
+        if len(tensors) != PDB_VIT_NUM_TENSORS:
+            raise NativeError(f"expected {PDB_VIT_NUM_TENSORS} tensors, got {len(tensors)}")
+        on_device = all(t.is_cuda for t in tensors)
+        keep = [t.detach().to(dtype=torch.float32).contiguous() if on_device else t.detach().to("cpu", torch.float32).contiguous()
+                for t in tensors]
+        arr = (C.c_void_p * len(keep))(*[C.c_void_p(t.data_ptr()) for t in keep])
+        numels = (C.c_int64 * len(keep))(*[t.numel() for t in keep])
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_vit_load(self.handle, arr, numels, len(keep), int(on_device), _stream_ptr(self.device)), "pdb_vit_load")
+        self.vit_key = None
+
+    def extract_features(self, images: torch.Tensor, scale_factors: Sequence[float], debug_stage: Optional[int] = None):
+        """images [n,3,H,W] in [0,1] -> z [n,384]; with debug_stage also the residual stream after that stage."""
+        n, ch, H, W = images.shape
+        if ch != 3:
+            raise NativeError(f"images must be [n,3,H,W], got {tuple(images.shape)}")
+        _check_dev(images, "images", self.device)
+        sf = (C.c_double * len(scale_factors))(*[float(f) for f in scale_factors])
+        z = torch.empty((n, VIT_DIM), device=self.device, dtype=torch.float32)
+        dbg = None
+        if debug_stage is not None:
+            rows = 0
+            for f in scale_factors:
+                oh, ow = (H, W) if f == 1 else (int(np.floor(H * float(f))), int(np.floor(W * float(f))))
+                rows += n * (1 + (oh // 16) * (ow // 16))
+            dbg = torch.empty((rows, VIT_DIM), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_extract_features(self.handle, C.c_void_p(images.data_ptr()), n, H, W, sf, len(scale_factors),
+                                                   C.c_void_p(z.data_ptr()), C.c_void_p(dbg.data_ptr()) if dbg is not None else None,
+                                                   int(debug_stage or 0), _stream_ptr(self.device)), "pdb_extract_features")
+        return (z, dbg) if debug_stage is not None else z
+
+    def extract_features_host(self, images: np.ndarray, scale_factors: Sequence[float]) -> np.ndarray:
+        n, ch, H, W = images.shape
+        if ch != 3 or images.dtype != np.float32 or not images.flags.c_contiguous:
+            raise NativeError("images must be contiguous float32 [n,3,H,W]")
+        sf = (C.c_double * len(scale_factors))(*[float(f) for f in scale_factors])
+        z = np.empty((n, VIT_DIM), dtype=np.float32)
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_extract_features_host(self.handle, images.ctypes.data_as(C.c_void_p), n, H, W, sf, len(scale_factors),
+                                                        z.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)), "pdb_extract_features_host")
+        return z
 
     # ---- denoiser / sampler -----------------------------------------------------------------------
     def denoiser_forward(self, x: torch.Tensor, t: int, z: torch.Tensor) -> torch.Tensor:

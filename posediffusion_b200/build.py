@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(PKG, "libposediff_b200.so")
-SOURCES = ["api_core.cu", "api_sampler.cu", "api_tc.cu"]
+SOURCES = ["api_core.cu", "api_sampler.cu", "api_tc.cu", "api_vit.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", f"-I{os.path.join(ROOT, 'include')}", f"-I{CSRC}"]
 
@@ -55,7 +55,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def run(cmd):
         res = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(OBJ, os.path.basename(cmd[-1]) + ".log")
+        log = os.path.join(OBJ, os.path.basename(cmd[cmd.index("-o") + 1]) + ".log")
         with open(log, "w") as fh:
             fh.write(res.stdout + res.stderr)
         if res.returncode != 0:

@@ -6,6 +6,7 @@
 
 #include "context.cuh"
 #include "denoiser.cuh"
+#include "fold_ln.cuh"
 #include "weights.cuh"
 
 using namespace pdb;
@@ -15,6 +16,7 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* po
                 pdb_ggs_stats* stats_dev, cudaStream_t st);
 
 int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st);
+void vit_release(Context* ctx);
 }  // namespace pdb
 
 constexpr int kTcMinTokens = 128;
@@ -59,31 +61,6 @@ __global__ void copy_cols_kernel(const float* __restrict__ W, int O, int ldw, in
   const int o = idx / Kpad, k = idx - o * Kpad;
   out[idx] = (k < Kuse) ? W[(size_t)o * ldw + c0 + k] : 0.f;
 }
-// LayerNorm folded into the following Linear:  LN(x) W^T + b = rstd (x Wf^T - mean colsum) + biasf  with
-// Wf = gamma * W (column-wise), colsum_o = sum_k Wf[o][k], biasf_o = b_o + sum_k beta_k W[o][k].  One block per output row.
-__global__ void fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, int K, float* __restrict__ Wf, float* __restrict__ colsum,
-                               float* __restrict__ biasf) {
-  const int o = blockIdx.x;
-  float cs = 0.f, bs = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float w = W[(size_t)o * K + k];
-    const float wf = w * gamma[k];
-    Wf[(size_t)o * K + k] = wf;
-    cs += wf;
-    bs += w * beta[k];
-  }
-  __shared__ float red[2][4];
-  cs = warp_sum(cs);
-  bs = warp_sum(bs);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cs; red[1][threadIdx.x >> 5] = bs; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    colsum[o] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-    biasf[o] = bias[o] + red[1][0] + red[1][1] + red[1][2] + red[1][3];
-  }
-}
-
 const int kShape[6][2] = {{128, 256}, {128, 0}, {128, 128}, {128, 0}, {512, 702}, {512, 0}};
 
 size_t tensor_floats(int i) {
@@ -206,6 +183,7 @@ void pdb_destroy(pdb_context* c) {
     if (ctx->weights->tc_arena) cudaFree(ctx->weights->tc_arena);
     delete ctx->weights;
   }
+  vit_release(ctx);
   if (ctx->ggs_ws) cudaFree(ctx->ggs_ws);
   if (ctx->den_ws) cudaFree(ctx->den_ws);
   if (ctx->stage) cudaFree(ctx->stage);

@@ -41,14 +41,12 @@ int make_map(Context* ctx, CUtensorMap* map, const float* ptr, int rows, int K, 
 namespace pdb {
 
 // Y = epilogue(X[S,K] @ W[O,K]^T) on the tensor cores.  K % 32 == 0, O % 64 == 0, all pointers 16-byte aligned.
-int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st) {
-  if (E.K % kTcBK || E.O % 64 || E.S < 1) return ctx->fail(PDB_ERR_INVALID, "tc_linear shape (S=%d, O=%d, K=%d)", E.S, E.O, E.K);
-  constexpr int BN = 64;
+template <int BN>
+static int launch_tc_linear(Context* ctx, const float* X, const float* W, const TcEpilogue& E, bool& attr, cudaStream_t st) {
   CUtensorMap mx, mw;
   if (int rc = make_map(ctx, &mx, X, E.S, E.K, kTcBM)) return rc;
   if (int rc = make_map(ctx, &mw, W, E.O, E.K, BN)) return rc;
   const size_t smem = tc_smem_bytes(BN);
-  bool& attr = ctx->attr_tc;
   if (!attr) {
     PDB_CUDA(ctx, cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
@@ -61,6 +59,15 @@ int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E
   PDB_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
   return PDB_OK;
+}
+
+// Y = epilogue(X[S,K] @ W[O,K]^T) on the tensor cores.  K % 32 == 0, O % 64 == 0, all pointers 16-byte aligned.
+// 128-feature tiles (UMMA 128x128x8) when they still fill the machine, 64-feature tiles for the small-S denoiser shapes.
+int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st) {
+  if (E.K % kTcBK || E.O % 64 || E.S < 1) return ctx->fail(PDB_ERR_INVALID, "tc_linear shape (S=%d, O=%d, K=%d)", E.S, E.O, E.K);
+  const long long wide_tiles = (long long)(E.O / 128) * ((E.S + kTcBM - 1) / kTcBM);
+  if (E.O % 128 == 0 && wide_tiles >= ctx->sm_count) return launch_tc_linear<128>(ctx, X, W, E, ctx->attr_tc128, st);
+  return launch_tc_linear<64>(ctx, X, W, E, ctx->attr_tc, st);
 }
 
 }  // namespace pdb

@@ -12,6 +12,7 @@
 namespace pdb {
 
 struct DenoiserWeights;  // denoiser.cuh
+struct VitWeights;       // api_vit.cu
 
 struct Context {
   int device = -1;
@@ -37,7 +38,12 @@ struct Context {
   int tc_graph_nodes = 0;
   // cudaFuncSetAttribute is per device: remember per context (= per device) what was already requested
   size_t attr_ggs[2] = {0, 0}, attr_den[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
-  bool attr_tc = false;
+  bool attr_tc = false, attr_tc128 = false;
+  // image feature extractor (csrc/api_vit.cu)
+  VitWeights* vit = nullptr;
+  void* vit_ws = nullptr;
+  size_t vit_ws_bytes = 0;
+  size_t attr_vit_att = 0;
   int denoiser_engine = 0;  // 0 auto, 1 fp32 persistent kernel, 2 tcgen05/TMA tiles (TF32)
   // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser
   bool profiling = false;

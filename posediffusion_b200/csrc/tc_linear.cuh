@@ -33,6 +33,7 @@ struct TcEpilogue {
   int ldy;
   int S, O, K;
   int relu;
+  int gelu;  // exact (erf) GELU, torch.nn.functional.gelu default
 };
 
 __host__ __device__ inline size_t tc_smem_bytes(int BN) {
@@ -189,6 +190,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
             for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
           }
+          if (E.gelu) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] = 0.5f * o[t] * (1.0f + erff(o[t] * 0.70710678118654752f));
+          }
           *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
@@ -201,5 +206,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
   }
 }
+
+struct Context;
+// Y = epilogue(X[S,K] @ W[O,K]^T) on the tensor cores (csrc/api_tc.cu).  K % 32 == 0, O % 64 == 0, 16-byte aligned pointers.
+int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st);
 
 }  // namespace pdb

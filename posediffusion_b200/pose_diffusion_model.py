@@ -2,9 +2,8 @@
 (models/pose_diffusion_model.py:35-142) for the inference branch.
 
 Hydra is not a dependency: the `_target_` strings of cfgs/default.yaml are resolved against this package
-(`models.Denoiser`, `models.GaussianDiffusion`, `models.TransformerEncoderWrapper`).  The image feature
-extractor (DINO ViT-S/16 from torch.hub) is upstream of the hot path: pass any module as
-IMAGE_FEATURE_EXTRACTOR, or call forward(z=...) with precomputed features.
+(`models.Denoiser`, `models.GaussianDiffusion`, `models.TransformerEncoderWrapper`,
+`models.MultiScaleImageFeatureExtractor`).  Features may also be passed precomputed as forward(z=...).
 """
 from __future__ import annotations
 
@@ -16,8 +15,10 @@ import torch.nn as nn
 from .camera_transform import pose_encoding_to_camera
 from .denoiser import Denoiser, TransformerEncoderWrapper
 from .gaussian_diffuser import GaussianDiffusion
+from .image_feature_extractor import MultiScaleImageFeatureExtractor
 
-_TARGETS = {"Denoiser": Denoiser, "GaussianDiffusion": GaussianDiffusion, "TransformerEncoderWrapper": TransformerEncoderWrapper}
+_TARGETS = {"Denoiser": Denoiser, "GaussianDiffusion": GaussianDiffusion, "TransformerEncoderWrapper": TransformerEncoderWrapper,
+            "MultiScaleImageFeatureExtractor": MultiScaleImageFeatureExtractor}
 
 
 def instantiate(cfg, **overrides):
