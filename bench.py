@@ -38,6 +38,8 @@ WORKLOADS = {
     "cfg2": (20, 0, "BASELINE configs[1]: 1 sequence x 20 frames per GPU, T=100, GGS off (denoiser-only path)"),
     "cfg5": (80, 4096, "BASELINE configs[4]: 1 sequence x 80 frames, T=100, GGS on, M=4096 x 6320 ordered pairs (25886720 matches)"),
 }
+FEATURES_DESC = ("widened row SURVEY 8f-2 (NOT the headline): MultiScaleImageFeatureExtractor = DINO ViT-S/16 at scales 1, 1/2, 1/3 over "
+                 "20 frames of 224x224 per sequence (264 tokens per frame), the stage that produces z for the sampler")
 ALGO_BYTES_PER_MATCH_EVAL = 16  # kp1.xy + kp2.xy as fp32
 
 
@@ -134,13 +136,138 @@ def cpu_reference_run(frames: int, per_pair: int, seed: int, threads: int, budge
 
 
 # ----------------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------------
+# Widened row: image features.  Same contract as the headline line, metric = images/s.
+# ----------------------------------------------------------------------------------------------------
+VIT_GEMM_FLOPS_PER_TOKEN = 2 * (768 * 384 + 12 * (384 * 1152 + 384 * 384 + 2 * 384 * 1536))
+VIT_TOKENS_PER_IMAGE = 197 + 50 + 17
+VIT_SCALES = [1, 1 / 2, 1 / 3]
+
+
+def cpu_features_run(n_images: int, seed: int, threads: int):
+    """The oracle port of the extractor (reference wrapper arithmetic + restated hub backbone) on the host cores."""
+    from oracle.dino_vit import DinoViTSmall16, multiscale_features
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    net = DinoViTSmall16().eval()
+    img = torch.rand(n_images, 3, 224, 224)
+    with torch.no_grad():
+        multiscale_features(net, img[:1], VIT_SCALES)
+        t0 = time.perf_counter()
+        multiscale_features(net, img, VIT_SCALES)
+        dt = time.perf_counter() - t0
+    return {"images_per_s": n_images / dt, "threads": threads, "sample": f"{n_images} frames of 224x224 at 3 scales in {dt:.2f} s"}
+
+
+def features_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    frames = 20 * args.seqs_per_gpu
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = cpu_features_run(64 * max(1, args.steps), args.seed, min(os.cpu_count() or 1, int(os.environ.get("PDB_REF_THREADS", "32"))))
+        print(json.dumps({"impl": "reference", "metric": "images/sec (DINO ViT-S/16 multi-scale features)", "value": res["images_per_s"],
+                          "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": FEATURES_DESC},
+                          "cpu_baseline": {"value": res["images_per_s"], "unit": "images/s", "cores": res["threads"], "kind": "port", "sample": res["sample"]},
+                          "e2e": {"value": res["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
+    import posediffusion_b200 as pdb
+    from posediffusion_b200 import _native
+    from posediffusion_b200.distributed import init_from_env, sequence_seed
+
+    rank, world, local = init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(args.seed)
+    ext = pdb.MultiScaleImageFeatureExtractor(modelname="dino_vits16", freeze=True, scale_factors=VIT_SCALES).to(dev)
+    img_host = torch.rand((frames, 3, 224, 224), generator=torch.Generator().manual_seed(sequence_seed(args.seed, rank))).pin_memory()
+    img_dev = img_host.to(dev)
+    ctx = _native.Context.get(dev)
+    ext(img_dev[:1].contiguous())  # loads the weights into the context
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        z = ctx.extract_features(img_dev, VIT_SCALES)
+    sync_all()
+    ctx.profile(True)
+    ctx.profile_read()
+    launches0 = ctx.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        sync_all()
+        for k in range(args.steps):
+            flush.zero_()
+            starts[k].record()
+            z = ctx.extract_features(img_dev, VIT_SCALES)
+            stops[k].record()
+        sync_all()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    _, _, gemm_ms, gemm_n = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launch_count - launches0
+    t_ms = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+    value = frames * world * args.steps / (float(t_ms.item()) / 1000.0)
+    img_np = img_host.numpy()
+    ctx.extract_features_host(img_np, VIT_SCALES)
+    sync_all()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        zh = ctx.extract_features_host(img_np, VIT_SCALES)
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - e0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return 0
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+    bf16 = float(peaks["bf16_tflops"]) if peaks else 2250.0
+    flops_call = frames * VIT_TOKENS_PER_IMAGE * VIT_GEMM_FLOPS_PER_TOKEN
+    achieved = flops_call * args.steps / (gemm_ms / 1000.0) / 1e12 if gemm_ms else None
+    line = {
+        "metric": "images/sec (DINO ViT-S/16 multi-scale features)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": float(t_ms.item()) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32 tensor-core products, f32 accumulate / residual stream / softmax / LayerNorm", "data": "synthetic",
+        "config": {"workload": FEATURES_DESC, "images_per_gpu": frames, "image": "224x224", "scale_factors": "1, 1/2, 1/3",
+                   "l2": "flushed between timed calls (256 MiB write)", "weights": "random init (hub init law), images ~ U(0,1)"},
+        "e2e": {"value": frames * world * args.steps / float(e2e_s.item()), "unit": "images/s", "h2d_bytes_per_step": int(img_host.numel() * 4),
+                "d2h_bytes_per_step": int(frames * 384 * 4), "note": "C-ABI pdb_extract_features_host from pinned host memory"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "roofline": {"kernel": "tc_linear_kernel (tcgen05.mma kind::tf32 + TMA; all projections of the backbone)", "bound": "tensor",
+                     "achieved": achieved, "peak": bf16 / 2, "unit": "TFLOP/s", "frac": achieved / (bf16 / 2) if achieved else None, "traffic": None,
+                     "peak_source": ("half of the measured dense bf16 rate (MEASURED_PEAKS.json bf16_tflops): TF32 runs at half the bf16 rate"
+                                     if peaks else "fallback: half of the nominal 2.25 PFLOP/s bf16 rate"),
+                     "algorithmic_flops_per_call": flops_call, "gemm_launches_per_call": gemm_n // max(1, args.steps),
+                     "gemm_ms_per_call": gemm_ms / max(1, args.steps),
+                     "note": "fp32 operands staged by TMA (4 B/element): the 128x128 tiles are bound by operand delivery from L2, not by the tensor pipe"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        res = cpu_features_run(96, args.seed, min(os.cpu_count() or 1, 32))
+        line["cpu_baseline"] = {"value": res["images_per_s"], "unit": "images/s", "cores": res["threads"], "kind": "port", "sample": res["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["features"])
     ap.add_argument("--seqs-per-gpu", type=int, default=1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU GGS iterations in the bounded sample")
@@ -148,6 +275,8 @@ def main():
     ap.add_argument("--denoiser-engine", default="auto", choices=["auto", "fp32", "tf32"],
                     help="auto = exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tiles (TF32) at or above")
     args = ap.parse_args()
+    if args.workload == "features":
+        return features_main(args)
     frames, per_pair, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

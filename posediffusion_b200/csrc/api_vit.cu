@@ -203,111 +203,135 @@ __global__ void vit_row_stats_kernel(const float* __restrict__ X, float* __restr
   }
 }
 
-// Multi-head self-attention of one (image, scale) sequence of L <= 256 tokens, head width 64.
-// CTA = (sequence, head, chunk of 64 query rows); K (row stride 68 floats: conflict-free 128-bit reads across keys) and V of the
-// head stay in shared memory; each warp processes 4 query rows at a time: lane j owns keys j, j+32, ... for the logits and the
-// softmax, then output columns (lane, lane+32) for the weighted sum of V.
-constexpr int kAttThreads = 256, kAttWarps = 8, kAttRows = 4, kAttChunk = 64, kAttKS = 68, kAttKeysPerLane = kVitMaxTokens / 32;
-__host__ __device__ inline size_t vit_att_smem_floats(int L) {
-  return (size_t)L * kAttKS + (size_t)L * kVitHD + (size_t)kAttWarps * L * kAttRows + (size_t)kAttWarps * kAttRows * kVitHD;
+// Multi-head self-attention of one (image, scale) sequence of L <= 256 tokens, head width 64, on the warp-level tensor-core path
+// (mma.sync m16n8k8 TF32, fp32 accumulate): the problem is 197 x 197 x 64 per head -- far below a 128-row tcgen05 tile pipeline's
+// break-even -- so each warp owns 16 query rows end to end and the logits never leave registers:
+//   S = (Q / 8) K^T   : A = Q fragments (registers, from global), B = K rows from shared memory (row stride 68 words: the 32
+//                       lanes of a B-fragment load hit 32 distinct banks), NT key tiles of 8 -> 4 accumulators per tile;
+//   softmax            : a query row lives in the 4 lanes of a quad -> two xor-shuffles per max / sum;
+//   O = P V            : the accumulator layout of S (row g: keys 2t, 2t+1) is reused directly as the A fragment of the second
+//                       product by permuting the summation index (k-slot t <-> key 2t, k-slot t+4 <-> key 2t+1) and reading V rows
+//                       in the same permuted order (again conflict-free with stride 68); no shuffles, no shared-memory round trip.
+// CTA = (sequence, head, 64 query rows) = 4 warps; K and V of the head are staged once per CTA (TF32-rounded, zero padded).
+constexpr int kAttThreads = 128, kAttChunk = 64, kAttStride = 68;
+__host__ __device__ inline size_t vit_att_smem_bytes(int nt) { return sizeof(uint32_t) * 2 * (size_t)nt * 8 * kAttStride; }
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
 }
-__global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int row0,
-                                                                   int L, int chunks) {
-  extern __shared__ __align__(16) float vsm[];
-  float* Ks = vsm;
-  float* Vs = Ks + (size_t)L * kAttKS;
-  float* Ps = Vs + (size_t)L * kVitHD;                 // [warp][L][4]
-  float* Qs = Ps + (size_t)kAttWarps * L * kAttRows;   // [warp][4][64]
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int NT>
+__global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int row0, int L,
+                                                                   int chunks) {
+  extern __shared__ __align__(16) uint32_t vsm[];
+  uint32_t* Ks = vsm;                          // [NT*8][68] TF32 bit patterns
+  uint32_t* Vs = vsm + NT * 8 * kAttStride;
   const int chunk = blockIdx.x % chunks, head = (blockIdx.x / chunks) % kVitHeads, seq = blockIdx.x / (chunks * kVitHeads);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t base = (size_t)(row0 + seq * L) * (3 * kVitDim);
-  for (int idx = threadIdx.x; idx < L * (kVitHD / 4); idx += kAttThreads) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const size_t base = (size_t)(row0 + seq * L) * (3 * kVitDim) + head * kVitHD;
+  for (int idx = threadIdx.x; idx < NT * 8 * (kVitHD / 4); idx += kAttThreads) {
     const int j = idx >> 4, c4 = idx & 15;
-    const float* src = qkv + base + (size_t)j * (3 * kVitDim) + head * kVitHD + c4 * 4;
-    *reinterpret_cast<float4*>(Ks + (size_t)j * kAttKS + c4 * 4) = *reinterpret_cast<const float4*>(src + kVitDim);
-    *reinterpret_cast<float4*>(Vs + (size_t)j * kVitHD + c4 * 4) = *reinterpret_cast<const float4*>(src + 2 * kVitDim);
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
+    if (j < L) {
+      const float* src = qkv + base + (size_t)j * (3 * kVitDim) + c4 * 4;
+      k4 = *reinterpret_cast<const float4*>(src + kVitDim);
+      v4 = *reinterpret_cast<const float4*>(src + 2 * kVitDim);
+    }
+    *reinterpret_cast<uint4*>(Ks + j * kAttStride + c4 * 4) = make_uint4(to_tf32(k4.x), to_tf32(k4.y), to_tf32(k4.z), to_tf32(k4.w));
+    *reinterpret_cast<uint4*>(Vs + j * kAttStride + c4 * 4) = make_uint4(to_tf32(v4.x), to_tf32(v4.y), to_tf32(v4.z), to_tf32(v4.w));
   }
   __syncthreads();
-  float* myP = Ps + (size_t)warp * L * kAttRows;
-  float* myQ = Qs + (size_t)warp * kAttRows * kVitHD;
-  const float scale = 0.125f;  // head_dim ** -0.5
-  for (int it = 0; it < kAttChunk / (kAttWarps * kAttRows); ++it) {
-    const int r0 = chunk * kAttChunk + it * (kAttWarps * kAttRows) + warp * kAttRows;
-    if (r0 >= L) break;  // warp-uniform
-    __syncwarp();
+  const int r_base = chunk * kAttChunk + warp * 16;
+  if (r_base >= L) return;  // whole warp; no block-level synchronisation follows
+  const int ra = r_base + g, rb = r_base + g + 8;
+  const float* qa = qkv + base + (size_t)min(ra, L - 1) * (3 * kVitDim);
+  const float* qb = qkv + base + (size_t)min(rb, L - 1) * (3 * kVitDim);
+  const float scale = 0.125f;  // head_dim ** -0.5, exact in TF32
+  uint32_t q[kVitHD / 8][4];
 #pragma unroll
-    for (int r = 0; r < kAttRows; ++r) {
-      const int row = min(r0 + r, L - 1);
-      const float2 q2 = *reinterpret_cast<const float2*>(qkv + base + (size_t)row * (3 * kVitDim) + head * kVitHD + lane * 2);
-      *reinterpret_cast<float2*>(myQ + r * kVitHD + lane * 2) = make_float2(q2.x * scale, q2.y * scale);
-    }
-    __syncwarp();
-    float s[kAttRows][kAttKeysPerLane];
-#pragma unroll
-    for (int r = 0; r < kAttRows; ++r)
-#pragma unroll
-      for (int i = 0; i < kAttKeysPerLane; ++i) s[r][i] = 0.f;
-#pragma unroll 2
-    for (int d4 = 0; d4 < kVitHD / 4; ++d4) {
-      float4 q[kAttRows];
-#pragma unroll
-      for (int r = 0; r < kAttRows; ++r) q[r] = *reinterpret_cast<const float4*>(myQ + r * kVitHD + d4 * 4);
-#pragma unroll
-      for (int i = 0; i < kAttKeysPerLane; ++i) {
-        const int j = lane + 32 * i;
-        if (32 * i < L) {  // warp-uniform
-          const float4 k4 = *reinterpret_cast<const float4*>(Ks + (size_t)min(j, L - 1) * kAttKS + d4 * 4);
-#pragma unroll
-          for (int r = 0; r < kAttRows; ++r)
-            s[r][i] = fmaf(q[r].x, k4.x, fmaf(q[r].y, k4.y, fmaf(q[r].z, k4.z, fmaf(q[r].w, k4.w, s[r][i]))));
-        }
-      }
-    }
-    float inv[kAttRows];
-#pragma unroll
-    for (int r = 0; r < kAttRows; ++r) {
-      float m = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < kAttKeysPerLane; ++i)
-        if (lane + 32 * i < L) m = fmaxf(m, s[r][i]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < kAttKeysPerLane; ++i) {
-        const float e = (lane + 32 * i < L) ? expf(s[r][i] - m) : 0.f;
-        s[r][i] = e;
-        sum += e;
-      }
-      inv[r] = 1.0f / warp_sum(sum);
-    }
-#pragma unroll
-    for (int i = 0; i < kAttKeysPerLane; ++i) {
-      const int j = lane + 32 * i;
-      if (j < L) *reinterpret_cast<float4*>(myP + (size_t)j * kAttRows) = make_float4(s[0][i] * inv[0], s[1][i] * inv[1], s[2][i] * inv[2], s[3][i] * inv[3]);
-    }
-    __syncwarp();
-    float o0[kAttRows], o1[kAttRows];
-#pragma unroll
-    for (int r = 0; r < kAttRows; ++r) o0[r] = o1[r] = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < L; ++j) {
-      const float4 p4 = *reinterpret_cast<const float4*>(myP + (size_t)j * kAttRows);
-      const float v0 = Vs[(size_t)j * kVitHD + lane], v1 = Vs[(size_t)j * kVitHD + 32 + lane];
-      o0[0] = fmaf(p4.x, v0, o0[0]); o1[0] = fmaf(p4.x, v1, o1[0]);
-      o0[1] = fmaf(p4.y, v0, o0[1]); o1[1] = fmaf(p4.y, v1, o1[1]);
-      o0[2] = fmaf(p4.z, v0, o0[2]); o1[2] = fmaf(p4.z, v1, o1[2]);
-      o0[3] = fmaf(p4.w, v0, o0[3]); o1[3] = fmaf(p4.w, v1, o1[3]);
-    }
-#pragma unroll
-    for (int r = 0; r < kAttRows; ++r) {
-      if (r0 + r < L) {
-        float* dst = att + (size_t)(row0 + seq * L + r0 + r) * kVitDim + head * kVitHD;
-        dst[lane] = o0[r];
-        dst[32 + lane] = o1[r];
-      }
-    }
+  for (int ks = 0; ks < kVitHD / 8; ++ks) {
+    q[ks][0] = to_tf32(qa[ks * 8 + t] * scale);
+    q[ks][1] = to_tf32(qb[ks * 8 + t] * scale);
+    q[ks][2] = to_tf32(qa[ks * 8 + t + 4] * scale);
+    q[ks][3] = to_tf32(qb[ks * 8 + t + 4] * scale);
   }
+  float s[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    const uint32_t* krow = Ks + (nt * 8 + g) * kAttStride + t;
+#pragma unroll
+    for (int ks = 0; ks < kVitHD / 8; ++ks) mma_tf32(s[nt], q[ks], krow[ks * 8], krow[ks * 8 + 4]);
+  }
+  // accumulator (g, 2t), (g, 2t+1) -> keys nt*8 + 2t, +1 of query row ra; (g+8, ..) -> the same keys of row rb
+  float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int k0 = nt * 8 + 2 * t;
+    if (k0 >= L) s[nt][0] = s[nt][2] = -INFINITY;
+    if (k0 + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
+    ma = fmaxf(ma, fmaxf(s[nt][0], s[nt][1]));
+    mb = fmaxf(mb, fmaxf(s[nt][2], s[nt][3]));
+  }
+  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+  mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+  mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = expf(s[nt][0] - ma);
+    s[nt][1] = expf(s[nt][1] - ma);
+    s[nt][2] = expf(s[nt][2] - mb);
+    s[nt][3] = expf(s[nt][3] - mb);
+    sa += s[nt][0] + s[nt][1];
+    sb += s[nt][2] + s[nt][3];
+  }
+  sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+  sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+  sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+  sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+  float o[kVitHD / 8][4];
+#pragma unroll
+  for (int dt = 0; dt < kVitHD / 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const uint32_t p[4] = {to_tf32(s[nt][0]), to_tf32(s[nt][2]), to_tf32(s[nt][1]), to_tf32(s[nt][3])};
+    const uint32_t* v0 = Vs + (nt * 8 + 2 * t) * kAttStride + g;
+#pragma unroll
+    for (int dt = 0; dt < kVitHD / 8; ++dt) mma_tf32(o[dt], p, v0[dt * 8], v0[kAttStride + dt * 8]);
+  }
+  const float ia = 1.0f / sa, ib = 1.0f / sb;
+  float* out = att + (size_t)(row0 + seq * L) * kVitDim + head * kVitHD + 2 * t;
+#pragma unroll
+  for (int dt = 0; dt < kVitHD / 8; ++dt) {
+    if (ra < L) *reinterpret_cast<float2*>(out + (size_t)ra * kVitDim + dt * 8) = make_float2(o[dt][0] * ia, o[dt][1] * ia);
+    if (rb < L) *reinterpret_cast<float2*>(out + (size_t)rb * kVitDim + dt * 8) = make_float2(o[dt][2] * ib, o[dt][3] * ib);
+  }
+}
+template <int NT>
+int launch_vit_attention(Context* ctx, const float* qkv, float* att, int row0, int L, int n_images, cudaStream_t st) {
+  static_assert(NT * 8 <= kVitMaxTokens, "key tiles");
+  const size_t smem = vit_att_smem_bytes(NT);
+  size_t& have = ctx->attr_vit_att[NT == 3 ? 0 : NT == 7 ? 1 : NT == 25 ? 2 : 3];
+  if (have < smem) {
+    PDB_CUDA(ctx, cudaFuncSetAttribute(vit_attention_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
+  const int chunks = (L + kAttChunk - 1) / kAttChunk;
+  vit_attention_kernel<NT><<<n_images * kVitHeads * chunks, kAttThreads, smem, st>>>(qkv, att, row0, L, chunks);
+  return PDB_OK;
+}
+int enqueue_vit_attention(Context* ctx, const float* qkv, float* att, int row0, int L, int n_images, cudaStream_t st) {
+  if (L <= 24) return launch_vit_attention<3>(ctx, qkv, att, row0, L, n_images, st);
+  if (L <= 56) return launch_vit_attention<7>(ctx, qkv, att, row0, L, n_images, st);
+  if (L <= 200) return launch_vit_attention<25>(ctx, qkv, att, row0, L, n_images, st);
+  return launch_vit_attention<32>(ctx, qkv, att, row0, L, n_images, st);
 }
 
 // z[n] = (1 / n_scales) * sum_scales LayerNorm(class row)  (vision_transformer forward: norm(x)[:, 0]; image_feature_extractor.py:74-83)
@@ -511,15 +535,6 @@ extern "C" int pdb_extract_features(pdb_context* c, const float* images_dev, int
   float* rstd = mean + pad64(S);
   float* Apatch = HID;
 
-  size_t att_smem = 0;
-  for (int s = 0; s < n_scales; ++s) att_smem = std::max(att_smem, sizeof(float) * vit_att_smem_floats(sc[s].tokens));
-  if (att_smem > ctx->smem_optin) return ctx->fail(PDB_ERR_LIMIT, "attention needs %zu bytes of shared memory", att_smem);
-  if (att_smem > ctx->attr_vit_att) {
-    PDB_CUDA(ctx, cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
-    ctx->attr_vit_att = att_smem;
-  }
-  const bool was_profiling = ctx->profiling;
-  ctx->profiling = false;  // the GEMM launches below are not denoiser launches
   auto lin = [&](const float* in, const float* Wm, int O, int K, const float* bias, const float* residual, const float* colsum, float* Y,
                  int gelu) {
     TcEpilogue E = {};
@@ -549,11 +564,8 @@ extern "C" int pdb_extract_features(pdb_context* c, const float* images_dev, int
     const VitLayer& L = w->layer[l];
     vit_row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(X, mean, rstd, S);
     if ((rc = lin(X, L.wqkv, 3 * kVitDim, kVitDim, L.bias_qkv, nullptr, L.colsum_qkv, QKV, 0))) break;
-    for (int s = 0; s < n_scales; ++s) {
-      const int Ls = sc[s].tokens, chunks = (Ls + kAttChunk - 1) / kAttChunk;
-      vit_attention_kernel<<<n_images * kVitHeads * chunks, kAttThreads, sizeof(float) * vit_att_smem_floats(Ls), st>>>(QKV, ATT, sc[s].row0,
-                                                                                                                    Ls, chunks);
-    }
+    for (int s = 0; s < n_scales && rc == PDB_OK; ++s) rc = enqueue_vit_attention(ctx, QKV, ATT, sc[s].row0, sc[s].tokens, n_images, st);
+    if (rc != PDB_OK) break;
     if ((rc = lin(ATT, L.wproj, kVitDim, kVitDim, L.bproj, X, nullptr, X, 0))) break;
     vit_row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(X, mean, rstd, S);
     if ((rc = lin(X, L.wfc1, kVitMlp, kVitDim, L.bias_fc1, nullptr, L.colsum_fc1, HID, 1))) break;
@@ -561,7 +573,6 @@ extern "C" int pdb_extract_features(pdb_context* c, const float* images_dev, int
     ctx->launches += 2 + n_scales;
     rc = dump(l + 1);
   }
-  ctx->profiling = was_profiling;
   if (rc != PDB_OK) return rc;
   vit_head_kernel<<<(n_images + 3) / 4, 128, 0, st>>>(X, head, w->norm_g, w->norm_b, n_images, z_dev);
   ctx->launches += 1;

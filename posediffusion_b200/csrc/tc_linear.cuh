@@ -5,6 +5,7 @@
 //     W into a 4-deep shared-memory ring, completion counted on mbarriers;
 //   * one elected thread issues `tcgen05.mma.cta_group::1.kind::tf32` (fp32 operands read as TF32, fp32 accumulate) with
 //     shared-memory descriptors, 4 K-steps of 8 per stage; the 128 x BN fp32 accumulator lives in TMEM;
+//   * the kernel is persistent over output tiles with a double-buffered TMEM accumulator (epilogue of tile i under the main loop of i+1);
 //   * `tcgen05.commit` releases ring slots / signals the epilogue; 4 epilogue warps read TMEM with `tcgen05.ld`
 //     (32 lanes x 32 columns per instruction) and apply bias / folded LayerNorm / residual / ReLU on the way to HBM.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (one TMEM lane quarter each).
@@ -16,7 +17,7 @@
 namespace pdb {
 
 constexpr int kTcThreads = 192;
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 4;  // default ring depth (64-feature tiles); the 128-feature variant may run 3 deep so that two CTAs share an SM
 constexpr int kTcBM = 128;  // tokens per tile  (UMMA M)
 constexpr int kTcBK = 32;   // floats per stage (128 bytes = one swizzle atom), 4 UMMA K-steps of 8
 
@@ -36,8 +37,8 @@ struct TcEpilogue {
   int gelu;  // exact (erf) GELU, torch.nn.functional.gelu default
 };
 
-__host__ __device__ inline size_t tc_smem_bytes(int BN) {
-  return (size_t)kTcStages * (kTcBM * 128 + BN * 128) + 256 + 1024;  // ring + barriers + alignment slack
+__host__ __device__ inline size_t tc_smem_bytes(int BN, int stages = kTcStages) {
+  return (size_t)stages * (kTcBM * 128 + BN * 128) + 256 + 1024;  // ring + barriers + alignment slack
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -84,7 +85,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN>
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: every CTA walks the tile list (tile = blockIdx.x, + gridDim.x, ...; feature-tile index fastest so that CTAs running
+// side by side share the same 128 token rows in L2).  The accumulator is double buffered in TMEM (2 x BN columns): while the four
+// epilogue warps drain tile i, the TMA and MMA warps are already inside tile i+1.
+template <int BN, int ST = kTcStages>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcEpilogue E) {
   static_assert(BN == 64 || BN == 128, "feature tile");
@@ -92,30 +100,35 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   constexpr uint32_t kABytes = kTcBM * 128, kBBytes = BN * 128, kStageBytes = kABytes + kBBytes;
-  const uint32_t bar_base = base + kTcStages * kStageBytes;
+  const uint32_t bar_base = base + ST * kStageBytes;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
-  auto empty_bar = [&](int s) { return bar_base + (kTcStages + s) * 8; };
-  const uint32_t tmem_full_bar = bar_base + 2 * kTcStages * 8;
-  const uint32_t tmem_slot = tmem_full_bar + 8;
+  auto empty_bar = [&](int s) { return bar_base + (ST + s) * 8; };
+  auto tmem_full_bar = [&](int b) { return bar_base + (2 * ST + b) * 8; };
+  auto tmem_empty_bar = [&](int b) { return bar_base + (2 * ST + 2 + b) * 8; };
+  const uint32_t tmem_slot = bar_base + (2 * ST + 4) * 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
   const int num_kb = E.K / kTcBK;
+  const int n_tiles = E.O / BN;
+  const int total_tiles = n_tiles * ((E.S + kTcBM - 1) / kTcBM);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < kTcStages; ++s) {
+    for (int s = 0; s < ST; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4 * 32);  // every epilogue thread arrives once it has read its part of the buffer
+    }
     mbar_fence_init();
   }
-  if (warp == 1) {  // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+  if (warp == 1) {  // TMEM allocation: two BN-column fp32 accumulators (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -125,76 +138,96 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), kStageBytes);
-        tma_load_2d(base + s * kStageBytes, &map_x, kb * kTcBK, m0, full_bar(s));
-        tma_load_2d(base + s * kStageBytes + kABytes, &map_w, kb * kTcBK, n0, full_bar(s));
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kTcBM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % ST;
+          const uint32_t ph = (it / ST) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), kStageBytes);
+          tma_load_2d(base + s * kStageBytes, &map_x, kb * kTcBK, m0, full_bar(s));
+          tma_load_2d(base + s * kStageBytes + kABytes, &map_w, kb * kTcBK, n0, full_bar(s));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
       const uint32_t idesc = umma_idesc_tf32(kTcBM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(tmem_empty_bar(buf), ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this buffer (passes at first use)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = umma_desc_k128(base + s * kStageBytes);
-        const uint64_t db = umma_desc_k128(base + s * kStageBytes + kABytes);
+        const uint32_t acc = tmem_acc + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % ST;
+          const uint32_t ph = (it / ST) & 1;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = umma_desc_k128(base + s * kStageBytes);
+          const uint64_t db = umma_desc_k128(base + s * kStageBytes + kABytes);
 #pragma unroll
-        for (int k = 0; k < kTcBK / 8; ++k)  // advance 8 floats = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
-          umma_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(empty_bar(s));  // frees the slot once the MMAs that read it have retired
+          for (int k = 0; k < kTcBK / 8; ++k)  // advance 8 floats = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
+            umma_tf32(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));  // frees the slot once the MMAs that read it have retired
+        }
+        umma_commit(tmem_full_bar(buf));  // accumulator complete
       }
-      umma_commit(tmem_full_bar);   // accumulator complete
     }
   } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int quarter = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + quarter * 32 + lane;
-    const bool row_ok = row < E.S;
     const float* bias = E.bias;
     if (bias && E.t_ptr) bias += (size_t)(*E.t_ptr) * E.bias_t_stride;
-    float mean = 0.f, rstd = 1.f;
-    if (E.colsum && row_ok) {
-      mean = E.row_mean[row];
-      rstd = E.row_rstd[row];
-    }
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / n_tiles) * kTcBM, n0 = (tile % n_tiles) * BN;
+      const int buf = lt & 1;
+      mbar_wait(tmem_full_bar(buf), (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < E.S;
+      float mean = 0.f, rstd = 1.f;
+      if (E.colsum && row_ok) {
+        mean = E.row_mean[row];
+        rstd = E.row_rstd[row];
+      }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      if (row_ok) {
-        float* yrow = E.Y + (size_t)row * E.ldy + n0 + c0;
-        const float* rrow = E.residual ? E.residual + (size_t)row * E.ldr + n0 + c0 : nullptr;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+        if (c0 + 32 == BN) {  // this thread's last read of the buffer: hand it back to the MMA warp before the global stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tmem_empty_bar(buf));
+        }
+        if (row_ok) {
+          float* yrow = E.Y + (size_t)row * E.ldy + n0 + c0;
+          const float* rrow = E.residual ? E.residual + (size_t)row * E.ldr + n0 + c0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int col = n0 + c0 + j + t;
-            float x = v[j + t];
-            if (E.colsum) x = rstd * (x - mean * __ldg(E.colsum + col));
-            if (bias) x += __ldg(bias + col);
-            o[t] = x;
-          }
-          if (rrow) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-          }
-          if (E.relu) {
+            for (int t = 0; t < 4; ++t) {
+              const int col = n0 + c0 + j + t;
+              float x = v[j + t];
+              if (E.colsum) x = rstd * (x - mean * __ldg(E.colsum + col));
+              if (bias) x += __ldg(bias + col);
+              o[t] = x;
+            }
+            if (rrow) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+            }
+            if (E.relu) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
-          }
-          if (E.gelu) {
+              for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
+            }
+            if (E.gelu) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) o[t] = 0.5f * o[t] * (1.0f + erff(o[t] * 0.70710678118654752f));
+              for (int t = 0; t < 4; ++t) o[t] = 0.5f * o[t] * (1.0f + erff(o[t] * 0.70710678118654752f));
+            }
+            *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
     }
@@ -203,7 +236,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
 

@@ -12,6 +12,12 @@ net = randomize(DinoViTSmall16(), VIT_SEED).eval()
 ctx = _native.Context.get("cuda:0")
 ctx.load_vit([v.cuda() for v in net.state_dict().values()])
 n, h, w, sf, seed = CASES["default"]
+if "--profile" in sys.argv:  # two calls at 20 frames for an ncu launch list
+    x = torch.rand(20, 3, 224, 224, device="cuda")
+    ctx.extract_features(x, sf)
+    ctx.extract_features(x, sf)
+    torch.cuda.synchronize()
+    sys.exit(0)
 img = images_for(n, h, w, seed)
 with torch.no_grad():
     zref, stages = multiscale_features(net, img, sf, return_stages=True)
