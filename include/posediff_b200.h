@@ -205,6 +205,21 @@ int pdb_extract_features(pdb_context* ctx, const float* images_dev, int32_t n_im
 int pdb_extract_features_host(pdb_context* ctx, const float* images_host, int32_t n_images, int32_t height, int32_t width,
                               const double* scale_factors, int32_t n_scales, float* z_host, void* stream);
 
+/* ---- post-loop geometry (widened row) -----------------------------------------------
+ * pose_encoding_to_camera for "absT_quaR_logFL" (util/camera_transform.py:64-105): pose_dev [count,9] -> R_dev [count,3,3]
+ * (pytorch3d quaternion_to_matrix, real part first, two_s = 2/|q|^2), T_dev [count,3], focal_dev [count,2] =
+ * clamp(exp(pose[7:9] + log_focal_length_bias), min_focal_length, max_focal_length) (defaults 1.8, 0.1, 20). */
+int pdb_pose_to_camera(pdb_context* ctx, const float* pose_dev, int32_t count, double log_focal_length_bias,
+                       double min_focal_length, double max_focal_length, float* R_dev, float* T_dev, float* focal_dev,
+                       void* stream);
+/* camera_to_rel_deg (util/metric.py:14-48): R/T of `batch` sequences of `frames` cameras ([batch*frames,3,3], [batch*frames,3],
+ * pytorch3d row-vector convention) -> r_deg_dev / t_deg_dev [batch * frames*(frames-1)/2]: relative rotation / translation
+ * direction error in degrees for every pair i < j (torch.combinations order, sequence major).  invalid_dev[0] becomes non-zero
+ * where the reference would raise ValueError (relative-rotation trace outside [-1-1e-4, 3+1e-4]). */
+int pdb_rel_pose_error(pdb_context* ctx, const float* R_pred_dev, const float* T_pred_dev, const float* R_gt_dev,
+                       const float* T_gt_dev, int32_t batch, int32_t frames, float* r_deg_dev, float* t_deg_dev,
+                       int32_t* invalid_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,3 +20,20 @@ class PerspectiveCameras(CamerasBase):
 
     def __len__(self):
         return self.R.shape[0]
+
+    def get_world_to_view_transform(self):
+        """pytorch3d row-vector convention: X_view = X_world @ R + T, i.e. the 4x4 matrix [[R, 0], [T, 1]]."""
+        R, T = torch.as_tensor(self.R), torch.as_tensor(self.T)
+        m = torch.zeros(R.shape[0], 4, 4, dtype=R.dtype, device=R.device)
+        m[:, :3, :3] = R
+        m[:, 3, :3] = T
+        m[:, 3, 3] = 1.0
+        return _Matrix(m)
+
+
+class _Matrix:
+    def __init__(self, m):
+        self._m = m
+
+    def get_matrix(self):
+        return self._m

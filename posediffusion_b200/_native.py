@@ -81,6 +81,8 @@ EXPORTS = {
     "pdb_sampson_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_ggs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(GgsConfig), C.c_void_p, C.c_void_p]),
     "pdb_sample_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_pose_to_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_rel_pose_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_vit_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_void_p]),
     "pdb_vit_pos_table": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "pdb_extract_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
@@ -252,6 +254,43 @@ class Context:
         arr = (C.c_void_p * len(keep))(*[C.c_void_p(t.data_ptr()) for t in keep])
         with torch.cuda.device(self.device):
             self._ok(self.lib.pdb_denoiser_load(self.handle, arr, len(keep), _stream_ptr(self.device)), "pdb_denoiser_load")
+
+    # ---- post-loop geometry ---------------------------------------------------------------------------
+    def pose_to_camera(self, pose: torch.Tensor, log_focal_length_bias=1.8, min_focal_length=0.1, max_focal_length=20.0):
+        """pose [..., 9] -> (R [n,3,3], T [n,3], focal [n,2]) with n = prod(leading dims)."""
+        flat = pose.reshape(-1, TARGET_DIM).to(torch.float32).contiguous()
+        _check_dev(flat, "pose", self.device)
+        n = flat.shape[0]
+        R = torch.empty((n, 3, 3), device=self.device, dtype=torch.float32)
+        T = torch.empty((n, 3), device=self.device, dtype=torch.float32)
+        F = torch.empty((n, 2), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_pose_to_camera(self.handle, C.c_void_p(flat.data_ptr()), n, float(log_focal_length_bias),
+                                                 float(min_focal_length), float(max_focal_length), C.c_void_p(R.data_ptr()),
+                                                 C.c_void_p(T.data_ptr()), C.c_void_p(F.data_ptr()), _stream_ptr(self.device)), "pdb_pose_to_camera")
+        return R, T, F
+
+    def rel_pose_error(self, R_pred, T_pred, R_gt, T_gt, batch: int):
+        """(r_deg, t_deg) [batch * N(N-1)/2] for `batch` sequences of N cameras; raises ValueError like pytorch3d's
+        so3_rotation_angle when a relative rotation has a trace outside the valid range."""
+        tensors = [t.to(torch.float32).contiguous() for t in (R_pred, T_pred, R_gt, T_gt)]
+        total = tensors[0].shape[0]
+        if batch < 1 or total % batch:
+            raise NativeError(f"{total} cameras do not split into {batch} sequences")
+        frames = total // batch
+        for t, name, shape in zip(tensors, ("R_pred", "T_pred", "R_gt", "T_gt"), ((total, 3, 3), (total, 3), (total, 3, 3), (total, 3))):
+            _check_dev(t, name, self.device, shape)
+        pairs = batch * frames * (frames - 1) // 2
+        r = torch.empty(pairs, device=self.device, dtype=torch.float32)
+        t = torch.empty(pairs, device=self.device, dtype=torch.float32)
+        flag = torch.zeros(1, device=self.device, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_rel_pose_error(self.handle, *[C.c_void_p(x.data_ptr()) for x in tensors], batch, frames,
+                                                 C.c_void_p(r.data_ptr()), C.c_void_p(t.data_ptr()), C.c_void_p(flag.data_ptr()),
+                                                 _stream_ptr(self.device)), "pdb_rel_pose_error")
+        if int(flag.item()):
+            raise ValueError("A matrix has trace outside valid range [-1-eps,3+eps].")
+        return r, t
 
     def load_vit(self, tensors: Sequence[torch.Tensor]):
         """DINO ViT-S/16 parameters in hub state_dict order (150 tensors, host or this device)."""

@@ -110,15 +110,28 @@ def test_product_never_imports_the_oracle():
                 assert "oracle/" not in text or f.endswith((".cuh", ".cu")), f
 
 
-def test_pose_encoding_to_camera():
+def test_pose_encoding_to_camera_host_contract():
+    """Unknown encodings raise ValueError like the reference (camera_transform.py:98-99); the conversion itself is native:
+    a CPU tensor is refused (the values are checked on the GPU in tests/test_gpu_post.py)."""
+    from posediffusion_b200 import _native
+
     pose = torch.randn(2, 4, 9)
-    cams = pdb.pose_encoding_to_camera(pose)
-    assert len(cams) == 8 and cams.R.shape == (8, 3, 3)
-    eye = cams.R @ cams.R.transpose(1, 2)
-    np.testing.assert_allclose(eye.numpy(), np.broadcast_to(np.eye(3), (8, 3, 3)), atol=1e-5)
-    assert (cams.focal_length >= 0.1).all() and (cams.focal_length <= 20).all()
     with pytest.raises(ValueError):
         pdb.pose_encoding_to_camera(pose, "other")
+    with pytest.raises(_native.NativeError):
+        pdb.pose_encoding_to_camera(pose)
+
+
+def test_auc_and_are_match_reference_golden(golden):
+    """Host-side reductions of util/metric.py restated in posediffusion_b200/metric.py, on the reference-generated fixture."""
+    from posediffusion_b200 import metric
+
+    g = golden("metrics.npz")
+    for name in ("b2n8", "b1n20", "b3n3"):
+        r, t = g[f"{name}_r_deg"], g[f"{name}_t_deg"]
+        assert abs(float(metric.calculate_auc_np(r, t, max_threshold=30)) - float(g[f"{name}_auc_np"])) < 1e-12
+        assert abs(float(metric.calculate_auc(torch.from_numpy(r), torch.from_numpy(t), max_threshold=30)) - float(g[f"{name}_auc"])) < 1e-6
+        np.testing.assert_allclose(metric.compute_ARE(torch.from_numpy(g[f"{name}_R"]), g[f"{name}_gt_R"]), g[f"{name}_are"], rtol=0, atol=1e-5)
 
 
 # ---- the kernels' geometry maths, executed on the host ------------------------------------------------
