@@ -27,11 +27,11 @@ def camera_to_rel_deg(pred_cameras, gt_cameras, device, batch_size):
 
 
 def calculate_auc_np(r_error, t_error, max_threshold=30):
-    """np.histogram of max(r, t) over integer bins [0, 1, ..., max_threshold], normalised, mean of the cumulative sum."""
-    r_error, t_error = np.asarray(r_error), np.asarray(t_error)
-    max_errors = np.maximum(r_error, t_error)
-    histogram, _ = np.histogram(max_errors, bins=np.arange(max_threshold + 1))
-    return np.mean(np.cumsum(histogram.astype(float) / float(len(max_errors))))
+    """Mean of the cumulative, pair-normalised histogram of max(r, t) over the integer-degree bins [k, k+1), k < max_threshold
+    (np.histogram semantics: the last bin is closed on the right, larger errors are not counted)."""
+    worst = np.maximum(np.asarray(r_error), np.asarray(t_error))
+    counts = np.histogram(worst, bins=np.arange(max_threshold + 1))[0].astype(float)
+    return np.mean(np.cumsum(counts / float(worst.shape[0])))
 
 
 def calculate_auc(r_error, t_error, max_threshold=30):
@@ -49,14 +49,13 @@ def calculate_auc(r_error, t_error, max_threshold=30):
     return torch.tensor(np.cumsum(normalized, dtype=np.float32).mean(dtype=np.float32))
 
 
+def _as_numpy(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
 def compute_ARE(rotation1, rotation2):
-    """Absolute rotation error in degrees per camera, folded to [0, 90] (min(err, |180 - err|))."""
-    if isinstance(rotation1, torch.Tensor):
-        rotation1 = rotation1.cpu().detach().numpy()
-    if isinstance(rotation2, torch.Tensor):
-        rotation2 = rotation2.cpu().detach().numpy()
-    R_rel = np.einsum("Bij,Bjk ->Bik", rotation1.transpose(0, 2, 1), rotation2)
-    t = (np.trace(R_rel, axis1=1, axis2=2) - 1) / 2
-    theta = np.arccos(np.clip(t, -1, 1))
-    error = theta * 180 / np.pi
-    return np.minimum(error, np.abs(180 - error))
+    """Absolute rotation error per camera in degrees: angle of R1^T R2, folded into [0, 90] by min(e, |180 - e|)."""
+    R1, R2 = _as_numpy(rotation1), _as_numpy(rotation2)
+    cos_angle = (np.einsum("bji,bji->b", R1, R2) - 1.0) / 2.0  # trace(R1^T R2) = sum_ij R1[j,i] R2[j,i]
+    degrees = np.degrees(np.arccos(np.clip(cos_angle, -1.0, 1.0)))
+    return np.minimum(degrees, np.abs(180.0 - degrees))

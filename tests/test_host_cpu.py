@@ -131,7 +131,9 @@ def test_auc_and_are_match_reference_golden(golden):
         r, t = g[f"{name}_r_deg"], g[f"{name}_t_deg"]
         assert abs(float(metric.calculate_auc_np(r, t, max_threshold=30)) - float(g[f"{name}_auc_np"])) < 1e-12
         assert abs(float(metric.calculate_auc(torch.from_numpy(r), torch.from_numpy(t), max_threshold=30)) - float(g[f"{name}_auc"])) < 1e-6
-        np.testing.assert_allclose(metric.compute_ARE(torch.from_numpy(g[f"{name}_R"]), g[f"{name}_gt_R"]), g[f"{name}_are"], rtol=0, atol=1e-5)
+        are, want = metric.compute_ARE(torch.from_numpy(g[f"{name}_R"]), g[f"{name}_gt_R"]), g[f"{name}_are"]
+        # fp32 trace, summed in a different order than the reference's matmul: 1e-3 degree, 0.05 degree next to 0 (acos at 1)
+        assert (np.abs(are - want) <= np.where(want < 1.0, 0.05, 1e-3)).all(), np.abs(are - want).max()
 
 
 # ---- the kernels' geometry maths, executed on the host ------------------------------------------------
