@@ -3,6 +3,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdint>
 
 #include "context.cuh"
 #include "tc_linear.cuh"
@@ -68,6 +69,8 @@ static int launch_tc_linear(Context* ctx, const float* X, const float* W, const 
 // 128-feature tiles (UMMA 128x128x8) when they still fill the machine, 64-feature tiles for the small-S denoiser shapes.
 int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st) {
   if (E.K % kTcBK || E.O % 64 || E.S < 1) return ctx->fail(PDB_ERR_INVALID, "tc_linear shape (S=%d, O=%d, K=%d)", E.S, E.O, E.K);
+  E.vec8 = (reinterpret_cast<uintptr_t>(E.Y) % 32 == 0) && (E.ldy % 8 == 0) &&
+           (!E.residual || (reinterpret_cast<uintptr_t>(E.residual) % 32 == 0 && E.ldr % 8 == 0));
   const long long wide_tiles = (long long)(E.O / 128) * ((E.S + kTcBM - 1) / kTcBM);
   if (E.O % 128 == 0 && wide_tiles >= ctx->sm_count) {
     // 3 x 32 KB ring: two CTAs per SM, the epilogue of one under the main loop of the other (measured 1.16-1.26x over 4 x 32 KB)

@@ -9,6 +9,7 @@
 //   12 x { row stats -> GEMM qkv (LayerNorm folded into the weights, applied in the epilogue) -> attention (shared memory,
 //          4 query rows per warp) -> GEMM proj (+residual) -> row stats -> GEMM fc1 (folded LN, exact GELU) -> GEMM fc2 (+residual) }
 //   head: final LayerNorm of the class rows, summed over scales in the reference's order, divided by the number of scales.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -225,16 +226,25 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+struct VitAttArgs {  // one launch covers every scale: CTA ranges [block0[s], block0[s+1]) belong to scale s
+  int n_scales;
+  int row0[kVitMaxScales], L[kVitMaxScales], chunks[kVitMaxScales], block0[kVitMaxScales + 1];
+};
 template <int NT>
-__global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int row0, int L,
-                                                                   int chunks) {
+__global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att,
+                                                                   const VitAttArgs A) {
   extern __shared__ __align__(16) uint32_t vsm[];
   uint32_t* Ks = vsm;                          // [NT*8][68] TF32 bit patterns
   uint32_t* Vs = vsm + NT * 8 * kAttStride;
-  const int chunk = blockIdx.x % chunks, head = (blockIdx.x / chunks) % kVitHeads, seq = blockIdx.x / (chunks * kVitHeads);
+  int sc = 0;
+  while (sc + 1 < A.n_scales && (int)blockIdx.x >= A.block0[sc + 1]) ++sc;
+  const int L = A.L[sc], chunks = A.chunks[sc], row0 = A.row0[sc];
+  const int local = blockIdx.x - A.block0[sc];
+  const int chunk = local % chunks, head = (local / chunks) % kVitHeads, seq = local / (chunks * kVitHeads);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tiles = (L + 7) >> 3;  // key tiles of this scale (<= NT); the unrolled loops below skip the rest (block-uniform)
   const size_t base = (size_t)(row0 + seq * L) * (3 * kVitDim) + head * kVitHD;
-  for (int idx = threadIdx.x; idx < NT * 8 * (kVitHD / 4); idx += kAttThreads) {
+  for (int idx = threadIdx.x; idx < tiles * 8 * (kVitHD / 4); idx += kAttThreads) {
     const int j = idx >> 4, c4 = idx & 15;
     float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
     if (j < L) {
@@ -264,9 +274,11 @@ __global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float*
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-    const uint32_t* krow = Ks + (nt * 8 + g) * kAttStride + t;
+    if (nt < tiles) {
+      const uint32_t* krow = Ks + (nt * 8 + g) * kAttStride + t;
 #pragma unroll
-    for (int ks = 0; ks < kVitHD / 8; ++ks) mma_tf32(s[nt], q[ks], krow[ks * 8], krow[ks * 8 + 4]);
+      for (int ks = 0; ks < kVitHD / 8; ++ks) mma_tf32(s[nt], q[ks], krow[ks * 8], krow[ks * 8 + 4]);
+    }
   }
   // accumulator (g, 2t), (g, 2t+1) -> keys nt*8 + 2t, +1 of query row ra; (g+8, ..) -> the same keys of row rb
   float ma = -INFINITY, mb = -INFINITY;
@@ -301,10 +313,12 @@ __global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float*
   for (int dt = 0; dt < kVitHD / 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    const uint32_t p[4] = {to_tf32(s[nt][0]), to_tf32(s[nt][2]), to_tf32(s[nt][1]), to_tf32(s[nt][3])};
-    const uint32_t* v0 = Vs + (nt * 8 + 2 * t) * kAttStride + g;
+    if (nt < tiles) {
+      const uint32_t p[4] = {to_tf32(s[nt][0]), to_tf32(s[nt][2]), to_tf32(s[nt][1]), to_tf32(s[nt][3])};
+      const uint32_t* v0 = Vs + (nt * 8 + 2 * t) * kAttStride + g;
 #pragma unroll
-    for (int dt = 0; dt < kVitHD / 8; ++dt) mma_tf32(o[dt], p, v0[dt * 8], v0[kAttStride + dt * 8]);
+      for (int dt = 0; dt < kVitHD / 8; ++dt) mma_tf32(o[dt], p, v0[dt * 8], v0[kAttStride + dt * 8]);
+    }
   }
   const float ia = 1.0f / sa, ib = 1.0f / sb;
   float* out = att + (size_t)(row0 + seq * L) * kVitDim + head * kVitHD + 2 * t;
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float*
   }
 }
 template <int NT>
-int launch_vit_attention(Context* ctx, const float* qkv, float* att, int row0, int L, int n_images, cudaStream_t st) {
+int launch_vit_attention(Context* ctx, const float* qkv, float* att, const VitAttArgs& A, cudaStream_t st) {
   static_assert(NT * 8 <= kVitMaxTokens, "key tiles");
   const size_t smem = vit_att_smem_bytes(NT);
   size_t& have = ctx->attr_vit_att[NT == 3 ? 0 : NT == 7 ? 1 : NT == 25 ? 2 : 3];
@@ -323,15 +337,17 @@ int launch_vit_attention(Context* ctx, const float* qkv, float* att, int row0, i
     PDB_CUDA(ctx, cudaFuncSetAttribute(vit_attention_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     have = smem;
   }
-  const int chunks = (L + kAttChunk - 1) / kAttChunk;
-  vit_attention_kernel<NT><<<n_images * kVitHeads * chunks, kAttThreads, smem, st>>>(qkv, att, row0, L, chunks);
+  vit_attention_kernel<NT><<<A.block0[A.n_scales], kAttThreads, smem, st>>>(qkv, att, A);
   return PDB_OK;
 }
-int enqueue_vit_attention(Context* ctx, const float* qkv, float* att, int row0, int L, int n_images, cudaStream_t st) {
-  if (L <= 24) return launch_vit_attention<3>(ctx, qkv, att, row0, L, n_images, st);
-  if (L <= 56) return launch_vit_attention<7>(ctx, qkv, att, row0, L, n_images, st);
-  if (L <= 200) return launch_vit_attention<25>(ctx, qkv, att, row0, L, n_images, st);
-  return launch_vit_attention<32>(ctx, qkv, att, row0, L, n_images, st);
+// one launch for all scales; the instantiation is chosen by the longest sequence (its key tiles live in registers)
+int enqueue_vit_attention(Context* ctx, const float* qkv, float* att, const VitAttArgs& A, cudaStream_t st) {
+  int L = 0;
+  for (int s = 0; s < A.n_scales; ++s) L = std::max(L, A.L[s]);
+  if (L <= 24) return launch_vit_attention<3>(ctx, qkv, att, A, st);
+  if (L <= 56) return launch_vit_attention<7>(ctx, qkv, att, A, st);
+  if (L <= 200) return launch_vit_attention<25>(ctx, qkv, att, A, st);
+  return launch_vit_attention<32>(ctx, qkv, att, A, st);
 }
 
 // z[n] = (1 / n_scales) * sum_scales LayerNorm(class row)  (vision_transformer forward: norm(x)[:, 0]; image_feature_extractor.py:74-83)
@@ -535,6 +551,14 @@ extern "C" int pdb_extract_features(pdb_context* c, const float* images_dev, int
   float* rstd = mean + pad64(S);
   float* Apatch = HID;
 
+  VitAttArgs att_args = {};
+  att_args.n_scales = n_scales;
+  for (int s = 0; s < n_scales; ++s) {
+    att_args.row0[s] = sc[s].row0;
+    att_args.L[s] = sc[s].tokens;
+    att_args.chunks[s] = (sc[s].tokens + kAttChunk - 1) / kAttChunk;
+    att_args.block0[s + 1] = att_args.block0[s] + n_images * kVitHeads * att_args.chunks[s];
+  }
   auto lin = [&](const float* in, const float* Wm, int O, int K, const float* bias, const float* residual, const float* colsum, float* Y,
                  int gelu) {
     TcEpilogue E = {};
@@ -564,13 +588,12 @@ extern "C" int pdb_extract_features(pdb_context* c, const float* images_dev, int
     const VitLayer& L = w->layer[l];
     vit_row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(X, mean, rstd, S);
     if ((rc = lin(X, L.wqkv, 3 * kVitDim, kVitDim, L.bias_qkv, nullptr, L.colsum_qkv, QKV, 0))) break;
-    for (int s = 0; s < n_scales && rc == PDB_OK; ++s) rc = enqueue_vit_attention(ctx, QKV, ATT, sc[s].row0, sc[s].tokens, n_images, st);
-    if (rc != PDB_OK) break;
+    if ((rc = enqueue_vit_attention(ctx, QKV, ATT, att_args, st))) break;
     if ((rc = lin(ATT, L.wproj, kVitDim, kVitDim, L.bproj, X, nullptr, X, 0))) break;
     vit_row_stats_kernel<<<(S + 7) / 8, 256, 0, st>>>(X, mean, rstd, S);
     if ((rc = lin(X, L.wfc1, kVitMlp, kVitDim, L.bias_fc1, nullptr, L.colsum_fc1, HID, 1))) break;
     if ((rc = lin(HID, L.wfc2, kVitDim, kVitMlp, L.bfc2, X, nullptr, X, 0))) break;
-    ctx->launches += 2 + n_scales;
+    ctx->launches += 3;
     rc = dump(l + 1);
   }
   if (rc != PDB_OK) return rc;

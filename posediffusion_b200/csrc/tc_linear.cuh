@@ -35,6 +35,7 @@ struct TcEpilogue {
   int S, O, K;
   int relu;
   int gelu;  // exact (erf) GELU, torch.nn.functional.gelu default
+  int vec8;  // set by the launcher: Y / residual rows are 32-byte aligned -> 256-bit global accesses
 };
 
 __host__ __device__ inline size_t tc_smem_bytes(int BN, int stages = kTcStages) {
@@ -85,6 +86,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void ld_global_v8(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float (&r)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]),
+               "f"(r[6]), "f"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -203,11 +215,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (row_ok) {
           float* yrow = E.Y + (size_t)row * E.ldy + n0 + c0;
           const float* rrow = E.residual ? E.residual + (size_t)row * E.ldr + n0 + c0 : nullptr;
+          // A thread owns one output row: 8 consecutive floats = one full 32-byte sector per access (256-bit LDG / STG), so
+          // the row-per-thread pattern at least never writes partial sectors (16-byte stores doubled the L2 write traffic).
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float o[4];
+          for (int j = 0; j < 32; j += 8) {
+            float o[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
               const int col = n0 + c0 + j + t;
               float x = v[j + t];
               if (E.colsum) x = rstd * (x - mean * __ldg(E.colsum + col));
@@ -215,18 +229,30 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               o[t] = x;
             }
             if (rrow) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+              float r[8];
+              if (E.vec8) {
+                ld_global_v8(rrow + j, r);
+              } else {
+                const float4 a = *reinterpret_cast<const float4*>(rrow + j), b = *reinterpret_cast<const float4*>(rrow + j + 4);
+                r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+              }
+#pragma unroll
+              for (int t = 0; t < 8; ++t) o[t] += r[t];
             }
             if (E.relu) {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) o[t] = fmaxf(o[t], 0.f);
+              for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
             }
             if (E.gelu) {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) o[t] = 0.5f * o[t] * (1.0f + erff(o[t] * 0.70710678118654752f));
+              for (int t = 0; t < 8; ++t) o[t] = 0.5f * o[t] * (1.0f + erff(o[t] * 0.70710678118654752f));
             }
-            *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
+            if (E.vec8) {
+              st_global_v8(yrow + j, o);
+            } else {
+              *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(yrow + j + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
           }
         }
       }
