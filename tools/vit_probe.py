@@ -12,6 +12,15 @@ net = randomize(DinoViTSmall16(), VIT_SEED).eval()
 ctx = _native.Context.get("cuda:0")
 ctx.load_vit([v.cuda() for v in net.state_dict().values()])
 n, h, w, sf, seed = CASES["default"]
+if "--sanitize" in sys.argv:  # small shapes for compute-sanitizer: backbone on 2 frames + the post-loop kernels
+    x = torch.rand(2, 3, 224, 224, device="cuda")
+    z = ctx.extract_features(x, sf)
+    z2 = ctx.extract_features(torch.rand(1, 3, 192, 224, device="cuda"), sf)
+    R, T, F = ctx.pose_to_camera(torch.randn(2, 5, 9, device="cuda"))
+    r, t = ctx.rel_pose_error(R, T, R.clone(), T.clone() + 0.1, 2)
+    torch.cuda.synchronize()
+    print("sanitize run ok", float(z.abs().mean()), float(z2.abs().mean()), float(r.mean()), float(t.mean()))
+    sys.exit(0)
 if "--profile" in sys.argv:  # two calls at 20 frames for an ncu launch list
     x = torch.rand(20, 3, 224, 224, device="cuda")
     ctx.extract_features(x, sf)
