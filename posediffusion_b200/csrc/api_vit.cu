@@ -208,14 +208,16 @@ __global__ void vit_row_stats_kernel(const float* __restrict__ X, float* __restr
 // (mma.sync m16n8k8 TF32, fp32 accumulate): the problem is 197 x 197 x 64 per head -- far below a 128-row tcgen05 tile pipeline's
 // break-even -- so each warp owns 16 query rows end to end and the logits never leave registers:
 //   S = (Q / 8) K^T   : A = Q fragments (registers, from global), B = K rows from shared memory (row stride 68 words: the 32
-//                       lanes of a B-fragment load hit 32 distinct banks), NT key tiles of 8 -> 4 accumulators per tile;
-//   softmax            : a query row lives in the 4 lanes of a quad -> two xor-shuffles per max / sum;
-//   O = P V            : the accumulator layout of S (row g: keys 2t, 2t+1) is reused directly as the A fragment of the second
+//                       lanes of a B-fragment load hit 32 distinct banks), in blocks of 8 key tiles (64 keys);
+//   softmax            : online (running max / sum per query row, rescaling the output accumulator per key block); a query row
+//                       lives in the 4 lanes of a quad -> two xor-shuffles per reduction;
+//   O += P V           : the accumulator layout of S (row g: keys 2t, 2t+1) is reused directly as the A fragment of the second
 //                       product by permuting the summation index (k-slot t <-> key 2t, k-slot t+4 <-> key 2t+1) and reading V rows
 //                       in the same permuted order (again conflict-free with stride 68); no shuffles, no shared-memory round trip.
-// CTA = (sequence, head, 64 query rows) = 4 warps; K and V of the head are staged once per CTA (TF32-rounded, zero padded).
-constexpr int kAttThreads = 128, kAttChunk = 64, kAttStride = 68;
-__host__ __device__ inline size_t vit_att_smem_bytes(int nt) { return sizeof(uint32_t) * 2 * (size_t)nt * 8 * kAttStride; }
+// CTA = (sequence, head, 128 query rows) = 8 warps; K and V of the head are staged once per CTA (TF32-rounded, zero padded).
+// 64-key blocks keep the kernel at <= 128 registers: two CTAs = 16 warps per SM.  One launch covers every scale.
+constexpr int kAttThreads = 256, kAttChunk = 128, kAttStride = 68, kAttKB = 8;
+__host__ __device__ inline size_t vit_att_smem_bytes(int tiles) { return sizeof(uint32_t) * 2 * (size_t)tiles * 8 * kAttStride; }
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -228,21 +230,21 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }
 struct VitAttArgs {  // one launch covers every scale: CTA ranges [block0[s], block0[s+1]) belong to scale s
   int n_scales;
+  int max_tiles;  // key tiles of the longest sequence (shared-memory carve-up)
   int row0[kVitMaxScales], L[kVitMaxScales], chunks[kVitMaxScales], block0[kVitMaxScales + 1];
 };
-template <int NT>
-__global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att,
-                                                                   const VitAttArgs A) {
+__global__ void __launch_bounds__(kAttThreads, 2) vit_attention_kernel(const float* __restrict__ qkv, float* __restrict__ att,
+                                                                      const VitAttArgs A) {
   extern __shared__ __align__(16) uint32_t vsm[];
-  uint32_t* Ks = vsm;                          // [NT*8][68] TF32 bit patterns
-  uint32_t* Vs = vsm + NT * 8 * kAttStride;
+  uint32_t* Ks = vsm;                          // [tiles*8][68] TF32 bit patterns
+  uint32_t* Vs = vsm + A.max_tiles * 8 * kAttStride;
   int sc = 0;
   while (sc + 1 < A.n_scales && (int)blockIdx.x >= A.block0[sc + 1]) ++sc;
   const int L = A.L[sc], chunks = A.chunks[sc], row0 = A.row0[sc];
   const int local = blockIdx.x - A.block0[sc];
   const int chunk = local % chunks, head = (local / chunks) % kVitHeads, seq = local / (chunks * kVitHeads);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int tiles = (L + 7) >> 3;  // key tiles of this scale (<= NT); the unrolled loops below skip the rest (block-uniform)
+  const int tiles = (L + 7) >> 3;  // key tiles of this scale
   const size_t base = (size_t)(row0 + seq * L) * (3 * kVitDim) + head * kVitHD;
   for (int idx = threadIdx.x; idx < tiles * 8 * (kVitHD / 4); idx += kAttThreads) {
     const int j = idx >> 4, c4 = idx & 15;
@@ -270,57 +272,74 @@ __global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float*
     q[ks][2] = to_tf32(qa[ks * 8 + t + 4] * scale);
     q[ks][3] = to_tf32(qb[ks * 8 + t + 4] * scale);
   }
-  float s[NT][4];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-    if (nt < tiles) {
-      const uint32_t* krow = Ks + (nt * 8 + g) * kAttStride + t;
-#pragma unroll
-      for (int ks = 0; ks < kVitHD / 8; ++ks) mma_tf32(s[nt], q[ks], krow[ks * 8], krow[ks * 8 + 4]);
-    }
-  }
-  // accumulator (g, 2t), (g, 2t+1) -> keys nt*8 + 2t, +1 of query row ra; (g+8, ..) -> the same keys of row rb
-  float ma = -INFINITY, mb = -INFINITY;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int k0 = nt * 8 + 2 * t;
-    if (k0 >= L) s[nt][0] = s[nt][2] = -INFINITY;
-    if (k0 + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
-    ma = fmaxf(ma, fmaxf(s[nt][0], s[nt][1]));
-    mb = fmaxf(mb, fmaxf(s[nt][2], s[nt][3]));
-  }
-  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
-  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
-  mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
-  mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
-  float sa = 0.f, sb = 0.f;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    s[nt][0] = expf(s[nt][0] - ma);
-    s[nt][1] = expf(s[nt][1] - ma);
-    s[nt][2] = expf(s[nt][2] - mb);
-    s[nt][3] = expf(s[nt][3] - mb);
-    sa += s[nt][0] + s[nt][1];
-    sb += s[nt][2] + s[nt][3];
-  }
-  sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-  sa += __shfl_xor_sync(0xffffffffu, sa, 2);
-  sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-  sb += __shfl_xor_sync(0xffffffffu, sb, 2);
   float o[kVitHD / 8][4];
 #pragma unroll
   for (int dt = 0; dt < kVitHD / 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+  float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;  // running max / (per-lane partial) sum of rows ra, rb
+#pragma unroll 1
+  for (int kb0 = 0; kb0 < tiles; kb0 += kAttKB) {  // block-uniform trip count; key kb0 * 8 < L is always valid
+    float s[kAttKB][4];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    if (nt < tiles) {
-      const uint32_t p[4] = {to_tf32(s[nt][0]), to_tf32(s[nt][2]), to_tf32(s[nt][1]), to_tf32(s[nt][3])};
-      const uint32_t* v0 = Vs + (nt * 8 + 2 * t) * kAttStride + g;
+    for (int nt = 0; nt < kAttKB; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (kb0 + nt < tiles) {
+        const uint32_t* krow = Ks + ((kb0 + nt) * 8 + g) * kAttStride + t;
 #pragma unroll
-      for (int dt = 0; dt < kVitHD / 8; ++dt) mma_tf32(o[dt], p, v0[dt * 8], v0[kAttStride + dt * 8]);
+        for (int ks = 0; ks < kVitHD / 8; ++ks) mma_tf32(s[nt], q[ks], krow[ks * 8], krow[ks * 8 + 4]);
+      }
+    }
+    // accumulator (g, 2t), (g, 2t+1) -> keys tile*8 + 2t, +1 of query row ra; (g+8, ..) -> the same keys of row rb
+    float bma = -INFINITY, bmb = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < kAttKB; ++nt) {
+      const int k0 = (kb0 + nt) * 8 + 2 * t;
+      if (k0 >= L) s[nt][0] = s[nt][2] = -INFINITY;
+      if (k0 + 1 >= L) s[nt][1] = s[nt][3] = -INFINITY;
+      bma = fmaxf(bma, fmaxf(s[nt][0], s[nt][1]));
+      bmb = fmaxf(bmb, fmaxf(s[nt][2], s[nt][3]));
+    }
+    bma = fmaxf(bma, __shfl_xor_sync(0xffffffffu, bma, 1));
+    bma = fmaxf(bma, __shfl_xor_sync(0xffffffffu, bma, 2));
+    bmb = fmaxf(bmb, __shfl_xor_sync(0xffffffffu, bmb, 1));
+    bmb = fmaxf(bmb, __shfl_xor_sync(0xffffffffu, bmb, 2));
+    const float na = fmaxf(ma, bma), nb = fmaxf(mb, bmb);            // finite: the block holds at least one valid key
+    const float alpha_a = expf(ma - na), alpha_b = expf(mb - nb);    // first block: exp(-inf) = 0
+    ma = na;
+    mb = nb;
+    float pa = 0.f, pb = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < kAttKB; ++nt) {
+      s[nt][0] = expf(s[nt][0] - ma);
+      s[nt][1] = expf(s[nt][1] - ma);
+      s[nt][2] = expf(s[nt][2] - mb);
+      s[nt][3] = expf(s[nt][3] - mb);
+      pa += s[nt][0] + s[nt][1];
+      pb += s[nt][2] + s[nt][3];
+    }
+    la = la * alpha_a + pa;
+    lb = lb * alpha_b + pb;
+#pragma unroll
+    for (int dt = 0; dt < kVitHD / 8; ++dt) {
+      o[dt][0] *= alpha_a;
+      o[dt][1] *= alpha_a;
+      o[dt][2] *= alpha_b;
+      o[dt][3] *= alpha_b;
+    }
+#pragma unroll
+    for (int nt = 0; nt < kAttKB; ++nt) {
+      if (kb0 + nt < tiles) {
+        const uint32_t p[4] = {to_tf32(s[nt][0]), to_tf32(s[nt][2]), to_tf32(s[nt][1]), to_tf32(s[nt][3])};
+        const uint32_t* v0 = Vs + ((kb0 + nt) * 8 + 2 * t) * kAttStride + g;
+#pragma unroll
+        for (int dt = 0; dt < kVitHD / 8; ++dt) mma_tf32(o[dt], p, v0[dt * 8], v0[kAttStride + dt * 8]);
+      }
     }
   }
-  const float ia = 1.0f / sa, ib = 1.0f / sb;
+  la += __shfl_xor_sync(0xffffffffu, la, 1);
+  la += __shfl_xor_sync(0xffffffffu, la, 2);
+  lb += __shfl_xor_sync(0xffffffffu, lb, 1);
+  lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+  const float ia = 1.0f / la, ib = 1.0f / lb;
   float* out = att + (size_t)(row0 + seq * L) * kVitDim + head * kVitHD + 2 * t;
 #pragma unroll
   for (int dt = 0; dt < kVitHD / 8; ++dt) {
@@ -328,26 +347,15 @@ __global__ void __launch_bounds__(kAttThreads) vit_attention_kernel(const float*
     if (rb < L) *reinterpret_cast<float2*>(out + (size_t)rb * kVitDim + dt * 8) = make_float2(o[dt][2] * ib, o[dt][3] * ib);
   }
 }
-template <int NT>
-int launch_vit_attention(Context* ctx, const float* qkv, float* att, const VitAttArgs& A, cudaStream_t st) {
-  static_assert(NT * 8 <= kVitMaxTokens, "key tiles");
-  const size_t smem = vit_att_smem_bytes(NT);
-  size_t& have = ctx->attr_vit_att[NT == 3 ? 0 : NT == 7 ? 1 : NT == 25 ? 2 : 3];
-  if (have < smem) {
-    PDB_CUDA(ctx, cudaFuncSetAttribute(vit_attention_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    have = smem;
-  }
-  vit_attention_kernel<NT><<<A.block0[A.n_scales], kAttThreads, smem, st>>>(qkv, att, A);
-  return PDB_OK;
-}
-// one launch for all scales; the instantiation is chosen by the longest sequence (its key tiles live in registers)
+// one launch for all scales; shared memory is sized by the longest sequence
 int enqueue_vit_attention(Context* ctx, const float* qkv, float* att, const VitAttArgs& A, cudaStream_t st) {
-  int L = 0;
-  for (int s = 0; s < A.n_scales; ++s) L = std::max(L, A.L[s]);
-  if (L <= 24) return launch_vit_attention<3>(ctx, qkv, att, A, st);
-  if (L <= 56) return launch_vit_attention<7>(ctx, qkv, att, A, st);
-  if (L <= 200) return launch_vit_attention<25>(ctx, qkv, att, A, st);
-  return launch_vit_attention<32>(ctx, qkv, att, A, st);
+  const size_t smem = vit_att_smem_bytes(A.max_tiles);
+  if (ctx->attr_vit_att[0] < smem) {
+    PDB_CUDA(ctx, cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->attr_vit_att[0] = smem;
+  }
+  vit_attention_kernel<<<A.block0[A.n_scales], kAttThreads, smem, st>>>(qkv, att, A);
+  return PDB_OK;
 }
 
 // z[n] = (1 / n_scales) * sum_scales LayerNorm(class row)  (vision_transformer forward: norm(x)[:, 0]; image_feature_extractor.py:74-83)
@@ -557,6 +565,7 @@ extern "C" int pdb_extract_features(pdb_context* c, const float* images_dev, int
     att_args.row0[s] = sc[s].row0;
     att_args.L[s] = sc[s].tokens;
     att_args.chunks[s] = (sc[s].tokens + kAttChunk - 1) / kAttChunk;
+    att_args.max_tiles = std::max(att_args.max_tiles, (sc[s].tokens + 7) / 8);
     att_args.block0[s + 1] = att_args.block0[s] + n_images * kVitHeads * att_args.chunks[s];
   }
   auto lin = [&](const float* in, const float* Wm, int O, int K, const float* bias, const float* residual, const float* colsum, float* Y,
