@@ -272,6 +272,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU GGS iterations in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ggs-layout", default="plain", choices=["plain", "paired"],
+                    help="HBM layout of the packed match stream (csrc/ggs_layout.cuh); 'paired' is experimental, see DESIGN.md 4.1")
     ap.add_argument("--denoiser-engine", default="auto", choices=["auto", "fp32", "tf32"],
                     help="auto = exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tiles (TF32) at or above")
     args = ap.parse_args()
@@ -323,6 +325,7 @@ def main():
     den = den.to(dev)
     ctx = den.native_context()
     ctx.set_denoiser_engine(args.denoiser_engine)
+    ctx.set_ggs_layout(args.ggs_layout)
     cfg = syn.default_ggs_cfg()
     cfg["verbose"] = False
     start_step = cfg["start_step"] if per_pair else 0
@@ -410,7 +413,7 @@ def main():
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if (args.denoiser_engine == "fp32" or (args.denoiser_engine == "auto" and B * frames < 128)) else "f32 (GGS, residual stream) + tf32 tensor-core products (denoiser projections)",
         "data": "synthetic",
-        "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "sequences_per_gpu": B, "denoiser_engine": args.denoiser_engine, "timesteps": T_STEPS,
+        "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "sequences_per_gpu": B, "denoiser_engine": args.denoiser_engine, "ggs_layout": args.ggs_layout, "timesteps": T_STEPS,
                    "parallelism": f"sequences sharded over {world} GPU(s), final all-gather of poses only",
                    "l2": "flushed between timed loops (256 MiB write); within a launch the match set is deliberately kept on chip when it fits",
                    "weights": "random init (reference init law), z ~ N(0,1), uniform-random correspondences"},

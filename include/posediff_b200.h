@@ -148,6 +148,20 @@ int pdb_matches_pack_colmap(pdb_context* ctx, int32_t n_images, const void* cons
 void pdb_matches_free(pdb_matches* m);
 int pdb_matches_info(const pdb_matches* m, int64_t* m_total, int32_t* segments, int64_t* rounds, int32_t* frames);
 
+/* Layout of the packed match stream in HBM for match sets packed on this context from now on (csrc/ggs_layout.cuh):
+ * 0 = plain (one float4 per match, segments padded to 32-row rounds; the default and the layout every round-1 number
+ * was measured with), 1 = paired (segments padded to 64-row units, the two matches of a lane component-interleaved so
+ * that the 128-bit loads are directly the operand pairs of the packed fp32x2 pipe).  Same 16 B per match, same results;
+ * the environment variable PDB_GGS_LAYOUT=paired selects 1 at pdb_create.  EXPERIMENTAL until measured on a B200. */
+int pdb_ggs_layout(pdb_context* ctx, int32_t layout);
+
+/* Host-only layout probe (no GPU, no context; test infrastructure): writes the stream image pdb_matches_pack would upload
+ * for reference-format matches -- segs_out [*nseg][4] = {first_round, count, frame_a, frame_b}, pts_out [*rounds * 32 * 4]
+ * floats.  With segs_out or pts_out NULL it only reports *nseg and *rounds.  PDB_ERR_LIMIT if the buffers are too small. */
+int pdb_debug_pack_layout(const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total, int32_t frames,
+                          int32_t layout, int32_t* segs_out, int32_t max_segs, float* pts_out, int64_t max_rounds,
+                          int32_t* nseg, int64_t* rounds);
+
 /* compute_sampson_distance + backward for one sequence: grad_dev[N,9] = d mean(valid err) / d pose,
  * scalars_dev[4] = {loss, n_valid, logged (= mean(min(err, max)) over all matches), 0}.  Optional per-segment
  * dumps: F_dev[segments,9] (F' = F^T), G_dev[segments,9] (sum over valid matches of d err / d F').

@@ -78,6 +78,9 @@ EXPORTS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "pdb_matches_free": (None, [C.c_void_p]),
     "pdb_matches_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "pdb_ggs_layout": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pdb_debug_pack_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "pdb_sampson_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_ggs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(GgsConfig), C.c_void_p, C.c_void_p]),
     "pdb_sample_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -130,6 +133,30 @@ def vit_pos_table(pos_embed: np.ndarray, grid_h: int, grid_w: int) -> np.ndarray
     if rc != 0:
         raise NativeError(f"pdb_vit_pos_table failed ({rc})")
     return out
+
+
+GGS_LAYOUTS = {"plain": 0, "paired": 1}
+
+
+def pack_layout_host(matches_dict: Dict, layout: str = "plain"):
+    """Host image of the packed match stream exactly as pdb_matches_pack lays it out in HBM (no GPU needed; used by the CPU
+    tests of the layout contract).  Returns (segs [nseg,4] int32 {first_round, count, a, b}, pts [rounds*32, 4] float32)."""
+    frames = int(matches_dict["img_shape"][0])
+    kp1 = np.ascontiguousarray(matches_dict["kp1"], dtype=np.float64).reshape(-1, 2)
+    kp2 = np.ascontiguousarray(matches_dict["kp2"], dtype=np.float64).reshape(-1, 2)
+    i12 = np.ascontiguousarray(matches_dict["i12"], dtype=np.int64).reshape(-1, 2)
+    lib = load_library()
+    nseg, rounds = C.c_int32(), C.c_int64()
+    args = (kp1.ctypes.data, kp2.ctypes.data, i12.ctypes.data, len(kp1), frames, GGS_LAYOUTS[layout])
+    rc = lib.pdb_debug_pack_layout(*args, None, 0, None, 0, C.byref(nseg), C.byref(rounds))
+    if rc != 0:
+        raise ValueError(f"pdb_debug_pack_layout failed ({rc})")
+    segs = np.zeros((max(nseg.value, 1), 4), dtype=np.int32)
+    pts = np.full((max(rounds.value, 1) * 32, 4), np.nan, dtype=np.float32)
+    rc = lib.pdb_debug_pack_layout(*args, segs.ctypes.data, nseg.value, pts.ctypes.data, rounds.value, C.byref(nseg), C.byref(rounds))
+    if rc != 0:
+        raise ValueError(f"pdb_debug_pack_layout failed ({rc})")
+    return segs[: nseg.value], pts[: rounds.value * 32]
 
 
 def ggs_config_struct(cfg: Dict) -> GgsConfig:
@@ -230,6 +257,10 @@ class Context:
     def set_denoiser_engine(self, mode: str = "auto"):
         """'auto' (fp32 kernel below 128 tokens, tensor cores above), 'fp32' or 'tf32'."""
         self._ok(self.lib.pdb_denoiser_engine(self.handle, {"auto": 0, "fp32": 1, "tf32": 2}[mode]), "pdb_denoiser_engine")
+
+    def set_ggs_layout(self, layout: str = "plain"):
+        """Stream layout of match sets packed from now on: 'plain' (default) or 'paired' (csrc/ggs_layout.cuh; experimental)."""
+        self._ok(self.lib.pdb_ggs_layout(self.handle, GGS_LAYOUTS[layout]), "pdb_ggs_layout")
 
     def tc_linear(self, x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, relu: bool = False) -> torch.Tensor:
         """Y = relu?(x @ w^T + bias + residual) on the tcgen05 tensor cores (TF32 products, fp32 accumulate)."""

@@ -20,7 +20,7 @@ struct GgsBatch {
   GgsProblem prob[kGgsBatchMax];
 };
 
-template <bool kEval>
+template <bool kEval, bool kPaired>
 __global__ void __launch_bounds__(kGgsThreads, 1)
 ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P);
 
@@ -72,6 +72,7 @@ int pdb_create(pdb_context** out, int device_ordinal) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (const char* lay = getenv("PDB_GGS_LAYOUT")) ctx->ggs_layout = (lay[0] == 'p' && lay[1] == 'a') ? kLayoutPaired : kLayoutPlain;
   *out = reinterpret_cast<pdb_context*>(ctx);
   return PDB_OK;
 }
@@ -143,11 +144,61 @@ int64_t pdb_launch_count(const pdb_context* c) { return c ? reinterpret_cast<con
 namespace {
 // Common tail of the packers: `segs` (without sentinel) are laid out in rounds, `row(src)` yields the fp32 quad of the
 // src-th match in segment order.  Fills pinned staging memory (threaded for big inputs), uploads, returns the handle.
+// Rows of segments [s0, s1) into the host image of the stream, in the given layout (ggs_layout.cuh); `first[s]` = index of
+// the segment's first match in segment order.
+template <typename Row>
+void fill_segments(const std::vector<int4>& segs, const std::vector<int64_t>& first, int s0, int s1, bool paired, float4* hpts, Row row) {
+  for (int s = s0; s < s1; ++s) {
+    const int64_t src0 = first[s];
+    const int cnt = segs[s].y;
+    if (!paired) {
+      float4* dst = hpts + (size_t)segs[s].x * 32;
+      const int padded = (cnt + 31) / 32 * 32;
+      for (int k = 0; k < cnt; ++k) dst[k] = row(src0 + k);
+      for (int k = cnt; k < padded; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      float* flat = reinterpret_cast<float*>(hpts);
+      const long long seg_rounds = layout_seg_rounds(cnt, true);
+      memset(hpts + (size_t)segs[s].x * 32, 0, sizeof(float4) * 32 * (size_t)seg_rounds);  // padding rows are zero
+      for (int k = 0; k < cnt; ++k) {
+        const float4 v = row(src0 + k);
+        flat[layout_float_index(segs[s].x, k, 0, true)] = v.x;
+        flat[layout_float_index(segs[s].x, k, 1, true)] = v.y;
+        flat[layout_float_index(segs[s].x, k, 2, true)] = v.z;
+        flat[layout_float_index(segs[s].x, k, 3, true)] = v.w;
+      }
+    }
+  }
+}
+
+// Pass 1 of pdb_matches_pack: maximal runs of equal (a, b) -> segments {first_round, count, a, b}; pair index a*N+b as the
+// reference (:26) computes it.  Returns the index of the first bad row, or -1.
+int64_t build_segments(const int64_t* i12, int64_t m_total, int frames, bool paired, std::vector<int4>& segs, long long* rounds_out) {
+  long long rounds = 0;
+  for (int64_t i = 0; i < m_total;) {
+    const int64_t a = i12[2 * i], b = i12[2 * i + 1];
+    if (a < 0 || a >= frames || b < 0 || b >= frames) return i;
+    int64_t j = i + 1;
+    while (j < m_total && i12[2 * j] == a && i12[2 * j + 1] == b) ++j;
+    int64_t remaining = j - i;
+    while (remaining > 0) {  // keep per-segment counts inside int32
+      const int64_t take = remaining > (1 << 30) ? (1 << 30) : remaining;
+      segs.push_back(make_int4((int)rounds, (int)take, (int)a, (int)b));
+      rounds += layout_seg_rounds(take, paired);
+      remaining -= take;
+    }
+    i = j;
+  }
+  *rounds_out = rounds;
+  return -1;
+}
+
 template <typename Row>
 int finish_pack(Context* ctx, std::vector<int4>& segs, long long rounds, int64_t m_total, int frames, int height, int width,
                 cudaStream_t st, pdb_matches** out, Row row) {
   if (rounds > 0x7fffffffLL / 32) return ctx->fail(PDB_ERR_LIMIT, "too many matches");
   const int nseg = (int)segs.size();
+  const bool paired = ctx->ggs_layout == kLayoutPaired;  // the callers sized the segments with the same flag
   segs.push_back(make_int4((int)rounds, 0, 0, 0));
   const size_t pts_bytes = sizeof(float4) * ((size_t)rounds * 32 ? (size_t)rounds * 32 : 1);
   const size_t segs_bytes = sizeof(int4) * segs.size();
@@ -165,15 +216,7 @@ int finish_pack(Context* ctx, std::vector<int4>& segs, long long rounds, int64_t
   {
     std::vector<int64_t> first(nseg + 1, 0);  // first match of each segment
     for (int s = 0; s < nseg; ++s) first[s + 1] = first[s] + segs[s].y;
-    auto fill = [&](int s0, int s1) {
-      for (int s = s0; s < s1; ++s) {
-        float4* dst = hpts + (size_t)segs[s].x * 32;
-        const int64_t src0 = first[s];
-        const int cnt = segs[s].y, padded = (cnt + 31) / 32 * 32;
-        for (int k = 0; k < cnt; ++k) dst[k] = row(src0 + k);
-        for (int k = cnt; k < padded; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
+    auto fill = [&](int s0, int s1) { fill_segments(segs, first, s0, s1, paired, hpts, row); };
     unsigned hw = std::thread::hardware_concurrency();
     int nthreads = m_total > 200000 ? (int)(hw < 8 ? (hw ? hw : 1) : 8) : 1;
     if (nthreads > nseg) nthreads = nseg > 0 ? nseg : 1;
@@ -198,6 +241,7 @@ int finish_pack(Context* ctx, std::vector<int4>& segs, long long rounds, int64_t
   m->ctx = ctx;
   m->nseg = nseg;
   m->rounds = (int)rounds;
+  m->layout = paired ? kLayoutPaired : kLayoutPlain;
   m->m_total = m_total;
   m->frames = frames;
   m->height = height;
@@ -254,25 +298,12 @@ int pdb_matches_pack(pdb_context* c, const double* kp1, const double* kp2, const
     kp2 = h2.data();
     i12 = hi.data();
   }
-  // pass 1: maximal runs of equal (a, b) -> segments; pair index a*N+b as the reference (:26) computes it
   std::vector<int4> segs;
   long long rounds = 0;
-  for (int64_t i = 0; i < m_total;) {
-    const int64_t a = i12[2 * i], b = i12[2 * i + 1];
-    if (a < 0 || a >= frames || b < 0 || b >= frames)
-      return ctx->fail(PDB_ERR_INVALID, "i12[%lld] = (%lld, %lld) outside [0, %d)", (long long)i, (long long)a, (long long)b, frames);
-    int64_t j = i + 1;
-    while (j < m_total && i12[2 * j] == a && i12[2 * j + 1] == b) ++j;
-    int64_t remaining = j - i, start = i;
-    while (remaining > 0) {  // keep per-segment counts inside int32
-      const int64_t take = remaining > (1 << 30) ? (1 << 30) : remaining;
-      segs.push_back(make_int4((int)rounds, (int)take, (int)a, (int)b));
-      rounds += (take + 31) / 32;
-      remaining -= take;
-      start += take;
-    }
-    i = j;
-  }
+  const int64_t bad = build_segments(i12, m_total, frames, ctx->ggs_layout == kLayoutPaired, segs, &rounds);
+  if (bad >= 0)
+    return ctx->fail(PDB_ERR_INVALID, "i12[%lld] = (%lld, %lld) outside [0, %d)", (long long)bad, (long long)i12[2 * bad],
+                     (long long)i12[2 * bad + 1], frames);
   return finish_pack(ctx, segs, rounds, m_total, frames, height, width, st, out, [&](int64_t src) {
     return make_float4((float)kp1[2 * src], (float)kp1[2 * src + 1], (float)kp2[2 * src], (float)kp2[2 * src + 1]);
   });
@@ -312,7 +343,7 @@ int pdb_matches_pack_colmap(pdb_context* c, int32_t n_images, const void* const*
     }
     segs.push_back(make_int4((int)rounds, cnt, r - 1, q - 1));  // i12 = (colmap_id - 1) (:69)
     seg_pair.push_back(p);
-    rounds += (cnt + 31) / 32;
+    rounds += layout_seg_rounds(cnt, ctx->ggs_layout == kLayoutPaired);
     m_total += cnt;
   }
   std::vector<int64_t> first(segs.size() + 1, 0);
@@ -350,19 +381,52 @@ int pdb_matches_info(const pdb_matches* pm, int64_t* m_total, int32_t* segments,
   return PDB_OK;
 }
 
+int pdb_ggs_layout(pdb_context* c, int32_t layout) {
+  if (!c) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  if (layout != kLayoutPlain && layout != kLayoutPaired) return ctx->fail(PDB_ERR_INVALID, "unknown stream layout %d", layout);
+  ctx->ggs_layout = layout;  // applies to match sets packed from now on; existing ones keep theirs
+  return PDB_OK;
+}
+
+// Host-only probe of the stream layout (no GPU, no context): lays reference-format matches out exactly as pdb_matches_pack
+// would place them in HBM.  The CPU tests walk this image with the kernel's own partition functions (ggs_layout.cuh).
+int pdb_debug_pack_layout(const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total, int32_t frames, int32_t layout,
+                          int32_t* segs_out, int32_t max_segs, float* pts_out, int64_t max_rounds, int32_t* nseg_out,
+                          int64_t* rounds_out) {
+  if (m_total < 0 || frames < 1 || (layout != kLayoutPlain && layout != kLayoutPaired) || !nseg_out || !rounds_out)
+    return PDB_ERR_INVALID;
+  if (m_total > 0 && (!kp1 || !kp2 || !i12)) return PDB_ERR_INVALID;
+  const bool paired = layout == kLayoutPaired;
+  std::vector<int4> segs;
+  long long rounds = 0;
+  if (build_segments(i12, m_total, frames, paired, segs, &rounds) >= 0) return PDB_ERR_INVALID;
+  *nseg_out = (int32_t)segs.size();
+  *rounds_out = rounds;
+  if (!segs_out || !pts_out) return PDB_OK;  // size query
+  if ((int64_t)segs.size() > max_segs || rounds > max_rounds) return PDB_ERR_LIMIT;
+  std::vector<int64_t> first(segs.size() + 1, 0);
+  for (size_t i = 0; i < segs.size(); ++i) first[i + 1] = first[i] + segs[i].y;
+  fill_segments(segs, first, 0, (int)segs.size(), paired, reinterpret_cast<float4*>(pts_out), [&](int64_t src) {
+    return make_float4((float)kp1[2 * src], (float)kp1[2 * src + 1], (float)kp2[2 * src], (float)kp2[2 * src + 1]);
+  });
+  memcpy(segs_out, segs.data(), sizeof(int4) * segs.size());
+  return PDB_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
 // GGS launch plumbing (shared with the sampler in api_sampler.cu)
 // ------------------------------------------------------------------------------------------------
 namespace {
-template <bool kEval>
+template <bool kEval, bool kPaired>
 __global__ void __launch_bounds__(kGgsThreads, 1)
 ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P) {
-  ggs_body<kEval>(batch.prob[blockIdx.x / P.ctas_per_problem], P);
+  ggs_body<kEval, kPaired>(batch.prob[blockIdx.x / P.ctas_per_problem], P);
 }
 
-template <bool kEval>
+template <bool kEval, bool kPaired>
 int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_frames, long long max_rounds,
                      GgsParams P, cudaStream_t st) {
   int cpp = ctx->sm_count / nprob;
@@ -374,16 +438,16 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   // shared-memory match cache: everything beyond the fixed per-frame state, in rounds of 512 B
   const size_t fixed = ggs_smem_fixed_bytes(max_frames);
   const size_t budget = ctx->smem_optin > fixed + 1024 ? ctx->smem_optin - fixed - 1024 : 0;
-  const long long rounds_per_cta = (max_rounds + cpp - 1) / cpp + 1;
+  const long long rounds_per_cta = ggs_rounds_per_cta(max_rounds, cpp, kPaired);
   // PDB_GGS_FORCE_STREAM=1 disables the shared-memory-resident mode (tests exercise the streaming ring with it)
   const char* force_stream = getenv("PDB_GGS_FORCE_STREAM");
   const bool resident = (size_t)rounds_per_cta * 512 <= budget && !(force_stream && force_stream[0] == '1');
   P.resident_rounds = resident ? (int)rounds_per_cta : 0;
   P.ring = resident ? 0 : 1;
   const size_t smem = fixed + (resident ? (size_t)rounds_per_cta * 512 : (size_t)kRingBytes);
-  size_t& attr_bytes = ctx->attr_ggs[kEval ? 1 : 0];
+  size_t& attr_bytes = ctx->attr_ggs[(kEval ? 1 : 0) + (kPaired ? 2 : 0)];
   if (smem > attr_bytes) {
-    PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval, kPaired>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
   cudaLaunchConfig_t cfg = {};
@@ -398,10 +462,18 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   cfg.numAttrs = 1;
   {
     ScopedTimer timer(ctx, st, 0);
-    PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ggs_entry<kEval>, batch, P));
+    PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ggs_entry<kEval, kPaired>, batch, P));
   }
   ctx->launches += 1;
   return PDB_OK;
+}
+
+// All match sets of one launch share a stream layout (it is a property of the context they were packed on).
+template <bool kEval>
+int launch_ggs_layout(Context* ctx, int layout, const GgsBatch& batch, int nprob, int max_frames, long long max_rounds,
+                      const GgsParams& P, cudaStream_t st) {
+  if (layout == kLayoutPaired) return launch_ggs_chunk<kEval, true>(ctx, batch, nprob, max_frames, max_rounds, P, st);
+  return launch_ggs_chunk<kEval, false>(ctx, batch, nprob, max_frames, max_rounds, P, st);
 }
 }  // namespace
 
@@ -419,6 +491,8 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* po
     const Matches* m = reinterpret_cast<const Matches*>(problems[b]);
     if (m->frames != reinterpret_cast<const Matches*>(problems[0])->frames)
       return ctx->fail(PDB_ERR_INVALID, "all sequences of a batch must have the same frame count");
+    if (m->layout != reinterpret_cast<const Matches*>(problems[0])->layout)
+      return ctx->fail(PDB_ERR_INVALID, "all match sets of a batch must use the same stream layout (pdb_ggs_layout)");
     max_frames = max_frames > m->frames ? max_frames : m->frames;
     ws_need += ggs_ws_per_problem(m->frames);
   }
@@ -464,7 +538,8 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* po
       ws += ggs_ws_per_problem(m->frames);
       max_rounds = max_rounds > m->rounds ? max_rounds : m->rounds;
     }
-    if (int rc = launch_ggs_chunk<false>(ctx, gb, nb, max_frames, max_rounds, P, st)) return rc;
+    const int layout = reinterpret_cast<const Matches*>(problems[b0])->layout;
+    if (int rc = launch_ggs_layout<false>(ctx, layout, gb, nb, max_frames, max_rounds, P, st)) return rc;
   }
   return PDB_OK;
 }
@@ -522,7 +597,7 @@ int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_de
   p.dbg_scalars = scalars_dev;
   p.dbg_F = F_dev;
   p.dbg_G = G_dev;
-  return launch_ggs_chunk<true>(ctx, gb, 1, m->frames, m->rounds > 0 ? m->rounds : 1, P, st);
+  return launch_ggs_layout<true>(ctx, m->layout, gb, 1, m->frames, m->rounds > 0 ? m->rounds : 1, P, st);
 }
 
 }  // extern "C"

@@ -37,13 +37,14 @@ struct Context {
   cudaStream_t tc_capture_stream = nullptr;
   int tc_graph_nodes = 0;
   // cudaFuncSetAttribute is per device: remember per context (= per device) what was already requested
-  size_t attr_ggs[2] = {0, 0}, attr_den[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
+  size_t attr_ggs[4] = {0, 0, 0, 0}, attr_den[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
   bool attr_tc = false, attr_tc128 = false;
   // image feature extractor (csrc/api_vit.cu)
   VitWeights* vit = nullptr;
   void* vit_ws = nullptr;
   size_t vit_ws_bytes = 0;
   size_t attr_vit_att[4] = {0, 0, 0, 0};
+  int ggs_layout = 0;       // stream layout of match sets packed on this context (ggs_layout.cuh): 0 plain, 1 paired
   int denoiser_engine = 0;  // 0 auto, 1 fp32 persistent kernel, 2 tcgen05/TMA tiles (TF32)
   // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser
   bool profiling = false;
@@ -75,6 +76,7 @@ struct Matches {
   int4* segs = nullptr;    // [nseg+1]
   int nseg = 0;
   int rounds = 0;
+  int layout = 0;          // kLayoutPlain / kLayoutPaired (ggs_layout.cuh)
   long long m_total = 0;
   int frames = 0;
   int height = 0, width = 0;

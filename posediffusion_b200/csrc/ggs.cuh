@@ -17,6 +17,7 @@
 //            norm-relative clip, momentum, update of its own copy of the pose.
 #pragma once
 #include "geom.cuh"
+#include "ggs_layout.cuh"
 #include "posediff_b200.h"
 
 namespace pdb {
@@ -75,12 +76,11 @@ __host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
 // Two matches per instruction: Blackwell's packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2) halves the issue slots of the
 // arithmetic that dominates stage 1.  Same formulas as `sampson_match` (geom.cuh) for two in-bounds rows A and B of the
 // same pair; acc2[k] holds separate partial sums for the two rows (merged at the segment end).
-__device__ __forceinline__ void sampson_match2(const float4 A, const float4 B, const float* __restrict__ F, float smax,
-                                               float2* __restrict__ acc2) {
+__device__ __forceinline__ void sampson_match2_core(const float2 u1, const float2 v1, const float2 u2, const float2 v2,
+                                                    const float* __restrict__ F, float smax, float2* __restrict__ acc2) {
   float2 F2[9];  // (F'[k], F'[k]): the packed pipe reads a scalar register as a broadcast pair (R.F32 operand form)
 #pragma unroll
   for (int k = 0; k < 9; ++k) F2[k] = make_float2(F[k], F[k]);
-  const float2 u1 = make_float2(A.x, B.x), v1 = make_float2(A.y, B.y), u2 = make_float2(A.z, B.z), v2 = make_float2(A.w, B.w);
   const float2 l0 = __ffma2_rn(u1, F2[0], __ffma2_rn(v1, F2[3], F2[6]));
   const float2 l1 = __ffma2_rn(u1, F2[1], __ffma2_rn(v1, F2[4], F2[7]));
   const float2 l2 = __ffma2_rn(u1, F2[2], __ffma2_rn(v1, F2[5], F2[8]));
@@ -107,11 +107,21 @@ __device__ __forceinline__ void sampson_match2(const float4 A, const float4 B, c
   acc2[7] = __fadd2_rn(acc2[7], w1);
   acc2[8] = __fadd2_rn(acc2[8], a);
 }
+// plain layout: the rows of two rounds, one float4 (u1,v1,u2,v2) each -> the compiler re-pairs the components (MOVs)
+__device__ __forceinline__ void sampson_match2(const float4 A, const float4 B, const float* __restrict__ F, float smax,
+                                               float2* __restrict__ acc2) {
+  sampson_match2_core(make_float2(A.x, B.x), make_float2(A.y, B.y), make_float2(A.z, B.z), make_float2(A.w, B.w), F, smax, acc2);
+}
+// paired layout (ggs_layout.cuh): X = (u1_A,u1_B,v1_A,v1_B), Y = (u2_A,u2_B,v2_A,v2_B) are already the operand pairs
+__device__ __forceinline__ void sampson_match2_unit(const float4 X, const float4 Y, const float* __restrict__ F, float smax,
+                                                    float2* __restrict__ acc2) {
+  sampson_match2_core(make_float2(X.x, X.y), make_float2(X.z, X.w), make_float2(Y.x, Y.y), make_float2(Y.z, Y.w), F, smax, acc2);
+}
 
 // One CTA of the group that owns one sequence.  See the file header for the stage structure.
 // `resident_rounds` > 0: the CTA's whole slice of matches (<= resident_rounds rounds) is staged in shared memory
 // once per launch and every inner iteration streams it from there (no L2/HBM traffic inside the loop).
-template <bool kEval>
+template <bool kEval, bool kPaired = false>
 __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,9 +152,9 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
 
   // ---- static work partition: rounds -> CTAs -> warps ----
   const long long R = pr.rounds;
-  const int r_cta0 = (int)(R * cta / cpp), r_cta1 = (int)(R * (cta + 1) / cpp);
-  const int r_w0 = r_cta0 + (int)((long long)(r_cta1 - r_cta0) * warp / kGgsWarps);
-  const int r_w1 = r_cta0 + (int)((long long)(r_cta1 - r_cta0) * (warp + 1) / kGgsWarps);
+  int r_cta0, r_cta1, r_w0, r_w1;  // paired layout: all four are even (whole units of two rounds)
+  ggs_cta_range(R, cta, cpp, kPaired, &r_cta0, &r_cta1);
+  ggs_warp_range(r_cta0, r_cta1, warp, kGgsWarps, kPaired, &r_w0, &r_w1);
   auto seg_of_round = [&](int r) {  // last segment whose first_round <= r
     int lo = 0, hi = pr.nseg;       // segs[nseg].x == rounds > r
     while (hi - lo > 1) {
@@ -335,12 +345,47 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
                   float4 pt[kGgsUnroll];
 #pragma unroll
                   for (int u = 0; u < kGgsUnroll; ++u) pt[u] = ring_ptr[(st * kGgsUnroll + u) * 32 + lane];
-                  if (kEval) {
+                  if constexpr (kPaired) {  // (pt[u], pt[u+1]) = (X, Y) of one unit: two matches per lane
+                    if (kEval) {
+#pragma unroll
+                      for (int u = 0; u < kGgsUnroll; u += 2) {
+                        sampson_match<kEval>(unit_match_a(pt[u], pt[u + 1]), Fm, true, P.smax, g);
+                        sampson_match<kEval>(unit_match_b(pt[u], pt[u + 1]), Fm, true, P.smax, g);
+                      }
+                    } else {
+#pragma unroll
+                      for (int u = 0; u < kGgsUnroll; u += 2) sampson_match2_unit(pt[u], pt[u + 1], Fm, P.smax, g2);
+                    }
+                  } else if (kEval) {
 #pragma unroll
                     for (int u = 0; u < kGgsUnroll; ++u) sampson_match<kEval>(pt[u], Fm, true, P.smax, g);
                   } else {
 #pragma unroll
                     for (int u = 0; u < kGgsUnroll; u += 2) sampson_match2(pt[u], pt[u + 1], Fm, P.smax, g2);
+                  }
+                } else if constexpr (kPaired) {
+#pragma unroll
+                  for (int u = 0; u < kGgsUnroll; u += 2) {
+                    const int q = q0 + u;  // even; r_w1 and every segment start are even, so the unit is whole
+                    if (q < r_w1) {        // warp-uniform
+                      if (q >= seg_end) {  // next pair segment (warp-uniform, rare)
+                        end_segment();
+                        ++s;
+                        sd = s_seg[s - cs];
+                        seg_end = s_seg[s - cs + 1].x;
+                        begin_segment();
+                      }
+                      const float4 X = ring_ptr[(st * kGgsUnroll + u) * 32 + lane];
+                      const float4 Y = ring_ptr[(st * kGgsUnroll + u + 1) * 32 + lane];
+                      const bool inb_a = (q - sd.x) * 32 + lane < sd.y, inb_b = (q + 1 - sd.x) * 32 + lane < sd.y;
+                      if (kEval) {
+                        sampson_match<kEval>(unit_match_a(X, Y), Fm, inb_a, P.smax, g);
+                        sampson_match<kEval>(unit_match_b(X, Y), Fm, inb_b, P.smax, g);
+                      } else {
+                        sampson_match<false, 2>(unit_match_a(X, Y), Fm, inb_a, P.smax, reinterpret_cast<float*>(g2));
+                        sampson_match<false, 2>(unit_match_b(X, Y), Fm, inb_b, P.smax, reinterpret_cast<float*>(g2));
+                      }
+                    }
                   }
                 } else {
 #pragma unroll
@@ -392,7 +437,34 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               const int nr = r_end - r;
               // rounds without padding rows (all but possibly the segment's last one) run a select-free body
               const int n_full = max(0, min(nr, seg_first + seg_count / 32 - r));
-              if (kEval) {
+              if constexpr (kPaired) {
+                // r, r_end and nr are even: the slice is a run of whole units (X = base[q*32], Y = base[(q+1)*32], q even)
+                const int n_full2 = n_full & ~1;  // rounds of the leading units without padding rows
+                if (kEval) {
+                  for (int q = 0; q < nr; q += 2) {
+                    const float4 X = base[q * 32], Y = base[(q + 1) * 32];
+                    const bool inb_a = (r + q - seg_first) * 32 + lane < seg_count;
+                    const bool inb_b = (r + q + 1 - seg_first) * 32 + lane < seg_count;
+                    sampson_match<kEval>(unit_match_a(X, Y), Fm, inb_a, P.smax, g);
+                    sampson_match<kEval>(unit_match_b(X, Y), Fm, inb_b, P.smax, g);
+                  }
+                } else {
+                  float2 g2[12];
+#pragma unroll
+                  for (int k = 0; k < 12; ++k) g2[k] = make_float2(0.f, 0.f);
+#pragma unroll 2
+                  for (int q = 0; q < n_full2; q += 2) sampson_match2_unit(base[q * 32], base[(q + 1) * 32], Fm, P.smax, g2);
+                  for (int q = n_full2; q < nr; q += 2) {
+                    const float4 X = base[q * 32], Y = base[(q + 1) * 32];
+                    const bool inb_a = (r + q - seg_first) * 32 + lane < seg_count;
+                    const bool inb_b = (r + q + 1 - seg_first) * 32 + lane < seg_count;
+                    sampson_match<false, 2>(unit_match_a(X, Y), Fm, inb_a, P.smax, reinterpret_cast<float*>(g2));
+                    sampson_match<false, 2>(unit_match_b(X, Y), Fm, inb_b, P.smax, reinterpret_cast<float*>(g2));
+                  }
+#pragma unroll
+                  for (int k = 0; k < 12; ++k) g[k] = g2[k].x + g2[k].y;
+                }
+              } else if (kEval) {
 #pragma unroll 4
                 for (int q = 0; q < n_full; ++q) sampson_match<kEval>(base[q * 32], Fm, true, P.smax, g);
                 for (int q = n_full; q < nr; ++q) {
@@ -424,12 +496,24 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
 #pragma unroll
                 for (int u = 0; u < kGgsUnroll; ++u)
                   if (r + kGgsUnroll + u < r_end) nxt[u] = ld_stream_f4(pr.pts + (size_t)(r + kGgsUnroll + u) * 32 + lane);
+                if constexpr (kPaired) {  // r and r_end are even: (cur[u], cur[u+1]) = (X, Y) of one whole unit
+#pragma unroll
+                  for (int u = 0; u < kGgsUnroll; u += 2) {
+                    if (r + u < r_end) {  // warp-uniform
+                      const bool inb_a = (r + u - seg_first) * 32 + lane < seg_count;
+                      const bool inb_b = (r + u + 1 - seg_first) * 32 + lane < seg_count;
+                      sampson_match<kEval>(unit_match_a(cur[u], cur[u + 1]), Fm, inb_a, P.smax, g);
+                      sampson_match<kEval>(unit_match_b(cur[u], cur[u + 1]), Fm, inb_b, P.smax, g);
+                    }
+                  }
+                } else {
 #pragma unroll
                 for (int u = 0; u < kGgsUnroll; ++u) {
                   if (r + u < r_end) {  // warp-uniform
                     const bool inb = (r + u - seg_first) * 32 + lane < seg_count;
                     sampson_match<kEval>(cur[u], Fm, inb, P.smax, g);
                   }
+                }
                 }
 #pragma unroll
                 for (int u = 0; u < kGgsUnroll; ++u) cur[u] = nxt[u];
