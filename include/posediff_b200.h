@@ -234,6 +234,14 @@ int pdb_rel_pose_error(pdb_context* ctx, const float* R_pred_dev, const float* T
                        const float* T_gt_dev, int32_t batch, int32_t frames, float* r_deg_dev, float* t_deg_dev,
                        int32_t* invalid_dev, void* stream);
 
+/* 7-dof ("Umeyama") alignment of predicted cameras to target cameras before the absolute rotation error
+ * (demo.py:126-128: pytorch3d.ops.corresponding_cameras_alignment(cameras_src, cameras_tgt, estimate_scale=True,
+ * mode="extrinsics", eps=1e-9); third-party algorithm restated in csrc/align.cuh).  R [count,3,3], T [count,3] in pytorch3d's
+ * row-vector convention; R_out / T_out = the aligned source cameras, align_dev[13] = {align_R (9), align_T (3), scale}. */
+int pdb_cameras_align(pdb_context* ctx, const float* R_src_dev, const float* T_src_dev, const float* R_tgt_dev,
+                      const float* T_tgt_dev, int32_t count, int32_t estimate_scale, double eps, float* R_out_dev,
+                      float* T_out_dev, float* align_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

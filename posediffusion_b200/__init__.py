@@ -5,6 +5,7 @@ Public surface mirrors the reference's (`models.PoseDiffusionModel`, `models.Gau
 `util.camera_transform.pose_encoding_to_camera`); compute goes through the C-ABI library
 `libposediff_b200.so` (include/posediff_b200.h).  No CPU or PyTorch-operator fallback exists.
 """
+from .camera_alignment import corresponding_cameras_alignment
 from .camera_transform import PerspectiveCameras, pose_encoding_to_camera
 from .denoiser import Denoiser, TransformerEncoderWrapper
 from .gaussian_diffuser import GaussianDiffusion
@@ -14,5 +15,5 @@ from .pose_diffusion_model import PoseDiffusionModel
 
 __all__ = [
     "PoseDiffusionModel", "GaussianDiffusion", "Denoiser", "TransformerEncoderWrapper", "MultiScaleImageFeatureExtractor",
-    "geometry_guided_sampling", "pose_encoding_to_camera", "PerspectiveCameras",
+    "geometry_guided_sampling", "pose_encoding_to_camera", "PerspectiveCameras", "corresponding_cameras_alignment",
 ]

@@ -86,6 +86,8 @@ EXPORTS = {
     "pdb_sample_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_pose_to_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_rel_pose_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_cameras_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_vit_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_void_p]),
     "pdb_vit_pos_table": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "pdb_extract_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
@@ -322,6 +324,21 @@ class Context:
         if int(flag.item()):
             raise ValueError("A matrix has trace outside valid range [-1-eps,3+eps].")
         return r, t
+
+    def cameras_align(self, R_src, T_src, R_tgt, T_tgt, estimate_scale: bool = True, eps: float = 1e-9):
+        """corresponding_cameras_alignment(mode="extrinsics") -> (R_aligned [n,3,3], T_aligned [n,3], align [13] = R | T | scale)."""
+        tensors = [t.to(torch.float32).contiguous() for t in (R_src, T_src, R_tgt, T_tgt)]
+        n = tensors[0].shape[0]
+        for t, name, shape in zip(tensors, ("R_src", "T_src", "R_tgt", "T_tgt"), ((n, 3, 3), (n, 3), (n, 3, 3), (n, 3))):
+            _check_dev(t, name, self.device, shape)
+        R = torch.empty((n, 3, 3), device=self.device, dtype=torch.float32)
+        T = torch.empty((n, 3), device=self.device, dtype=torch.float32)
+        align = torch.empty(13, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._ok(self.lib.pdb_cameras_align(self.handle, *[C.c_void_p(x.data_ptr()) for x in tensors], n, int(bool(estimate_scale)),
+                                                float(eps), C.c_void_p(R.data_ptr()), C.c_void_p(T.data_ptr()),
+                                                C.c_void_p(align.data_ptr()), _stream_ptr(self.device)), "pdb_cameras_align")
+        return R, T, align
 
     def load_vit(self, tensors: Sequence[torch.Tensor]):
         """DINO ViT-S/16 parameters in hub state_dict order (150 tensors, host or this device)."""

@@ -2,6 +2,7 @@
 // reference's evaluation computes from them.  Tiny, latency-bound work: one thread per camera / per pair, no staging.
 #include <cmath>
 
+#include "align.cuh"
 #include "context.cuh"
 
 using namespace pdb;
@@ -95,7 +96,81 @@ __global__ void rel_pose_error_kernel(const float* __restrict__ Rp, const float*
   t_deg[idx] = err * 180.0f / 3.14159265358979323846f;
 }
 
+// corresponding_cameras_alignment, mode "extrinsics" (csrc/align.cuh).  Estimate: ONE warp; lanes stride over the cameras, two
+// passes (means, then centred second moments, as the reference computes them), lane 0 finishes with the 3x3 SVD.
+// align[13] = {align_R (9, row-major), align_T (3), s}.
+__global__ void cameras_align_estimate_kernel(const float* __restrict__ Rs, const float* __restrict__ Ts, const float* __restrict__ Rt,
+                                              const float* __restrict__ Tt, int count, int estimate_scale, float eps,
+                                              float* __restrict__ align) {
+  const int lane = threadIdx.x;
+  float P[9], A[3], B[3], sum[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) sum[k] = 0.f;
+  for (int i = lane; i < count; i += 32) {
+    align_camera_terms(Rs + (size_t)i * 9, Ts + (size_t)i * 3, Rt + (size_t)i * 9, Tt + (size_t)i * 3, P, A, B);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sum[k] += P[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      sum[9 + k] += A[k];
+      sum[12 + k] += B[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 15; ++k) sum[k] = warp_sum(sum[k]) / (float)count;  // every lane holds the means
+  float scale = 1.f;
+  if (estimate_scale && count > 1) {
+    float ab = 0.f, aa = 0.f;
+    for (int i = lane; i < count; i += 32) {
+      align_camera_terms(Rs + (size_t)i * 9, Ts + (size_t)i * 3, Rt + (size_t)i * 9, Tt + (size_t)i * 3, P, A, B);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float ac = A[k] - sum[9 + k], bc = B[k] - sum[12 + k];
+        ab = fmaf(ac, bc, ab);
+        aa = fmaf(ac, ac, aa);
+      }
+    }
+    ab = warp_sum(ab) / (float)(3 * count);
+    aa = warp_sum(aa) / (float)(3 * count);
+    scale = ab / fmaxf(aa, eps);  // (Ac * Bc).mean() / (Ac ** 2).mean().clamp(eps)
+  }
+  if (lane == 0) {
+    svd3_v_ut(sum, align);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) align[9 + k] = sum[12 + k] - scale * sum[9 + k];
+    align[12] = scale;
+  }
+}
+
+__global__ void cameras_align_apply_kernel(const float* __restrict__ align, const float* __restrict__ Rs, const float* __restrict__ Ts,
+                                           int count, float* __restrict__ Ro, float* __restrict__ To) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float al[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) al[k] = align[k];
+  align_apply_camera(al, Rs + (size_t)i * 9, Ts + (size_t)i * 3, Ro + (size_t)i * 9, To + (size_t)i * 3);
+}
+
 }  // namespace
+
+extern "C" int pdb_cameras_align(pdb_context* c, const float* R_src_dev, const float* T_src_dev, const float* R_tgt_dev,
+                                 const float* T_tgt_dev, int32_t count, int32_t estimate_scale, double eps, float* R_out_dev,
+                                 float* T_out_dev, float* align_dev, void* stream) {
+  if (!c) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  if (!R_src_dev || !T_src_dev || !R_tgt_dev || !T_tgt_dev || !R_out_dev || !T_out_dev || !align_dev)
+    return ctx->fail(PDB_ERR_INVALID, "null argument");
+  if (count < 1) return ctx->fail(PDB_ERR_INVALID, "count %d", count);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cameras_align_estimate_kernel<<<1, 32, 0, st>>>(R_src_dev, T_src_dev, R_tgt_dev, T_tgt_dev, count, estimate_scale, (float)eps, align_dev);
+  PDB_CUDA(ctx, cudaGetLastError());
+  cameras_align_apply_kernel<<<(count + 127) / 128, 128, 0, st>>>(align_dev, R_src_dev, T_src_dev, count, R_out_dev, T_out_dev);
+  PDB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 2;
+  return PDB_OK;
+}
 
 extern "C" int pdb_pose_to_camera(pdb_context* c, const float* pose_dev, int32_t count, double log_focal_length_bias,
                                   double min_focal_length, double max_focal_length, float* R_dev, float* T_dev, float* focal_dev,

@@ -322,3 +322,42 @@ extern "C" int ggs_host_walk(const float* pts, const int* segs, int nseg, long l
 extern "C" long long layout_float_index_host(long long first_round, long long k, int comp, int paired) {
   return (long long)layout_float_index(first_round, k, comp, paired != 0);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// csrc/align.cuh on the host: the camera alignment exactly as the two kernels of csrc/api_post.cu compute it
+// (means, centred second moments, V U^T by one-sided Jacobi, application), sequentially.
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../posediffusion_b200/csrc/align.cuh"
+
+extern "C" void svd3_v_ut_host(const float* M, float* out) { svd3_v_ut(M, out); }
+
+extern "C" void cameras_align_host(const float* Rs, const float* Ts, const float* Rt, const float* Tt, int count, int estimate_scale,
+                                   float eps, float* Ro, float* To, float* align) {
+  float P[9], A[3], B[3], sum[15];
+  for (int k = 0; k < 15; ++k) sum[k] = 0.f;
+  for (int i = 0; i < count; ++i) {
+    align_camera_terms(Rs + i * 9, Ts + i * 3, Rt + i * 9, Tt + i * 3, P, A, B);
+    for (int k = 0; k < 9; ++k) sum[k] += P[k];
+    for (int k = 0; k < 3; ++k) { sum[9 + k] += A[k]; sum[12 + k] += B[k]; }
+  }
+  for (int k = 0; k < 15; ++k) sum[k] /= (float)count;
+  float scale = 1.f;
+  if (estimate_scale && count > 1) {
+    float ab = 0.f, aa = 0.f;
+    for (int i = 0; i < count; ++i) {
+      align_camera_terms(Rs + i * 9, Ts + i * 3, Rt + i * 9, Tt + i * 3, P, A, B);
+      for (int k = 0; k < 3; ++k) {
+        const float ac = A[k] - sum[9 + k], bc = B[k] - sum[12 + k];
+        ab = fmaf(ac, bc, ab);
+        aa = fmaf(ac, ac, aa);
+      }
+    }
+    ab /= (float)(3 * count);
+    aa /= (float)(3 * count);
+    scale = ab / fmaxf(aa, eps);
+  }
+  svd3_v_ut(sum, align);
+  for (int k = 0; k < 3; ++k) align[9 + k] = sum[12 + k] - scale * sum[9 + k];
+  align[12] = scale;
+  for (int i = 0; i < count; ++i) align_apply_camera(align, Rs + i * 9, Ts + i * 3, Ro + i * 9, To + i * 3);
+}
