@@ -26,5 +26,10 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:ggs_
   python tools/ggs_stage_probe.py 80 4096 paired > gpurun_out/ncu_cfg5_paired.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ggs_entry -s 2 -c 1 -f -o gpurun_out/ggs_cfg3_paired \
   python tools/ggs_stage_probe.py 20 2048 paired > gpurun_out/ncu_cfg3_paired.log 2>&1
+# tensor-core engine at a size where the projections are real GEMMs (512 sequences x 20 frames = 10 240 tokens, GGS off):
+# steps/s and the tensor-pipe share of tc_linear_kernel (sm__pipe_tensor_cycles_active) for DESIGN 4.3
+timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload cfg2 --seqs-per-gpu 512 > gpurun_out/bench_cfg2_b512.json 2> gpurun_out/bench_cfg2_b512.err
+timeout 600 ncu --set full --clock-control none -k regex:tc_linear -s 200 -c 6 -f -o gpurun_out/tc_linear_b512 \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --workload cfg2 --seqs-per-gpu 512 > gpurun_out/ncu_tc_b512.log 2>&1
 tail -n 3 gpurun_out/exp_tests.log
 for f in gpurun_out/bench_*_*.json; do echo "$f: $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['value'], d.get('kernel_ms_per_loop'), (d.get('roofline') or {}).get('frac'))" 2>&1)"; done
