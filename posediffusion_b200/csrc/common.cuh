@@ -63,8 +63,29 @@ __device__ __forceinline__ int warp_reduce16_slot(int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Memory helpers
+// Memory helpers, mbarrier + bulk asynchronous copy
 // ---------------------------------------------------------------------------------------------
+#ifdef PDB_EMU
+// TEST HARNESS ONLY (tests/host/cuda_emu.h): the inline-PTX helpers below restated for the CPU emulation that runs these
+// kernels unmodified on the host.  Never defined in a product build (nvcc does not see PDB_EMU).
+inline float4 ld_stream_f4(const float4* p) { return *p; }
+inline unsigned ld_acquire_u32(const unsigned* p) {
+  sched_yield();  // the poller spins on another OS thread's progress
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
+inline unsigned ld_relaxed_u32(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void red_release_add_u32(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+inline uint32_t smem_u32(const void* p) { return emu::shared_addr(p); }
+inline void mbar_init(uint32_t bar, uint32_t count) { emu::mbar_init(bar, count); }
+inline void mbar_fence_init() {}
+inline void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) { emu::mbar_arrive_expect_tx(bar, bytes); }
+inline bool mbar_try_wait(uint32_t bar, uint32_t parity) { return emu::mbar_try_wait(bar, parity); }
+inline void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+inline void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) { emu::bulk_copy_g2s(dst_smem, src, bytes, bar); }
+#else
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -81,9 +102,7 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// ---------------------------------------------------------------------------------------------
 // mbarrier + bulk asynchronous copy (global -> shared, completion counted in bytes on an mbarrier)
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -110,14 +129,15 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-
-// The same barrier executed by ONE warp per CTA (the rest of the CTA waits at a later __syncthreads).
-// All 32 lanes may have issued global atomics before; __syncwarp orders them before lane 0's release.
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+#endif
+
+// The same barrier executed by ONE warp per CTA (the rest of the CTA waits at a later __syncthreads).
+// All 32 lanes may have issued global atomics before; __syncwarp orders them before lane 0's release.
 __device__ __forceinline__ void warp_group_barrier(unsigned* counter, unsigned target) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {

@@ -123,7 +123,11 @@ __device__ __forceinline__ void sampson_match2_unit(const float4 X, const float4
 // once per launch and every inner iteration streams it from there (no L2/HBM traffic inside the loop).
 template <bool kEval, bool kPaired = false>
 __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& P) {
+#ifdef PDB_EMU  // tests/host/cuda_emu.h (CPU emulation of this kernel, test harness only): dynamic shared memory of this CTA
+  unsigned char* const smem_raw = emu::g_cta->smem;
+#else
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cpp = P.ctas_per_problem;
   const int cta = blockIdx.x % cpp;
