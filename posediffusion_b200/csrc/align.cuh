@@ -108,4 +108,63 @@ PDB_HD void align_apply_camera(const float* al, const float* Rs, const float* Ts
   for (int c = 0; c < 3; ++c) To[c] = al[9] * Rs[0 + c] + al[10] * Rs[3 + c] + al[11] * Rs[6 + c] + al[12] * Ts[c];
 }
 
+// ---- kernel bodies (device side; csrc/api_post.cu wraps them in __global__ functions, tests/host/align_emu.cpp runs them on
+// the CPU emulation of the execution model) ----
+// Estimate: ONE warp; lanes stride over the cameras, two passes (means, then centred second moments, as the reference computes
+// them), lane 0 finishes with the 3x3 SVD.  align[13] = {align_R (9, row-major), align_T (3), s}.
+__device__ __forceinline__ void cameras_align_estimate_warp(const float* __restrict__ Rs, const float* __restrict__ Ts,
+                                                            const float* __restrict__ Rt, const float* __restrict__ Tt, int count,
+                                                            int estimate_scale, float eps, float* __restrict__ align) {
+  const int lane = threadIdx.x;
+  float P[9], A[3], B[3], sum[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) sum[k] = 0.f;
+  for (int i = lane; i < count; i += 32) {
+    align_camera_terms(Rs + (size_t)i * 9, Ts + (size_t)i * 3, Rt + (size_t)i * 9, Tt + (size_t)i * 3, P, A, B);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sum[k] += P[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      sum[9 + k] += A[k];
+      sum[12 + k] += B[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 15; ++k) sum[k] = warp_sum(sum[k]) / (float)count;  // every lane holds the means
+  float scale = 1.f;
+  if (estimate_scale && count > 1) {
+    float ab = 0.f, aa = 0.f;
+    for (int i = lane; i < count; i += 32) {
+      align_camera_terms(Rs + (size_t)i * 9, Ts + (size_t)i * 3, Rt + (size_t)i * 9, Tt + (size_t)i * 3, P, A, B);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float ac = A[k] - sum[9 + k], bc = B[k] - sum[12 + k];
+        ab = fmaf(ac, bc, ab);
+        aa = fmaf(ac, ac, aa);
+      }
+    }
+    ab = warp_sum(ab) / (float)(3 * count);
+    aa = warp_sum(aa) / (float)(3 * count);
+    scale = ab / fmaxf(aa, eps);  // (Ac * Bc).mean() / (Ac ** 2).mean().clamp(eps)
+  }
+  if (lane == 0) {
+    svd3_v_ut(sum, align);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) align[9 + k] = sum[12 + k] - scale * sum[9 + k];
+    align[12] = scale;
+  }
+}
+
+// Application: one thread per camera.
+__device__ __forceinline__ void cameras_align_apply_thread(const float* __restrict__ align, const float* __restrict__ Rs,
+                                                           const float* __restrict__ Ts, int count, float* __restrict__ Ro,
+                                                           float* __restrict__ To) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float al[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) al[k] = align[k];
+  align_apply_camera(al, Rs + (size_t)i * 9, Ts + (size_t)i * 3, Ro + (size_t)i * 9, To + (size_t)i * 3);
+}
+
 }  // namespace pdb

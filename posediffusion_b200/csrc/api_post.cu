@@ -96,60 +96,16 @@ __global__ void rel_pose_error_kernel(const float* __restrict__ Rp, const float*
   t_deg[idx] = err * 180.0f / 3.14159265358979323846f;
 }
 
-// corresponding_cameras_alignment, mode "extrinsics" (csrc/align.cuh).  Estimate: ONE warp; lanes stride over the cameras, two
-// passes (means, then centred second moments, as the reference computes them), lane 0 finishes with the 3x3 SVD.
-// align[13] = {align_R (9, row-major), align_T (3), s}.
+// corresponding_cameras_alignment, mode "extrinsics": bodies in csrc/align.cuh (shared with the CPU emulation harness)
 __global__ void cameras_align_estimate_kernel(const float* __restrict__ Rs, const float* __restrict__ Ts, const float* __restrict__ Rt,
                                               const float* __restrict__ Tt, int count, int estimate_scale, float eps,
                                               float* __restrict__ align) {
-  const int lane = threadIdx.x;
-  float P[9], A[3], B[3], sum[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) sum[k] = 0.f;
-  for (int i = lane; i < count; i += 32) {
-    align_camera_terms(Rs + (size_t)i * 9, Ts + (size_t)i * 3, Rt + (size_t)i * 9, Tt + (size_t)i * 3, P, A, B);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) sum[k] += P[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      sum[9 + k] += A[k];
-      sum[12 + k] += B[k];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 15; ++k) sum[k] = warp_sum(sum[k]) / (float)count;  // every lane holds the means
-  float scale = 1.f;
-  if (estimate_scale && count > 1) {
-    float ab = 0.f, aa = 0.f;
-    for (int i = lane; i < count; i += 32) {
-      align_camera_terms(Rs + (size_t)i * 9, Ts + (size_t)i * 3, Rt + (size_t)i * 9, Tt + (size_t)i * 3, P, A, B);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float ac = A[k] - sum[9 + k], bc = B[k] - sum[12 + k];
-        ab = fmaf(ac, bc, ab);
-        aa = fmaf(ac, ac, aa);
-      }
-    }
-    ab = warp_sum(ab) / (float)(3 * count);
-    aa = warp_sum(aa) / (float)(3 * count);
-    scale = ab / fmaxf(aa, eps);  // (Ac * Bc).mean() / (Ac ** 2).mean().clamp(eps)
-  }
-  if (lane == 0) {
-    svd3_v_ut(sum, align);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) align[9 + k] = sum[12 + k] - scale * sum[9 + k];
-    align[12] = scale;
-  }
+  cameras_align_estimate_warp(Rs, Ts, Rt, Tt, count, estimate_scale, eps, align);
 }
 
 __global__ void cameras_align_apply_kernel(const float* __restrict__ align, const float* __restrict__ Rs, const float* __restrict__ Ts,
                                            int count, float* __restrict__ Ro, float* __restrict__ To) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  float al[13];
-#pragma unroll
-  for (int k = 0; k < 13; ++k) al[k] = align[k];
-  align_apply_camera(al, Rs + (size_t)i * 9, Ts + (size_t)i * 3, Ro + (size_t)i * 9, To + (size_t)i * 3);
+  cameras_align_apply_thread(align, Rs, Ts, count, Ro, To);
 }
 
 }  // namespace

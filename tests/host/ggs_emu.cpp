@@ -4,6 +4,7 @@
 #include "cuda_emu.h"
 
 #include "../../posediffusion_b200/csrc/ggs.cuh"
+#include "../../posediffusion_b200/csrc/align.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // emulator runtime
@@ -135,4 +136,13 @@ extern "C" int ggs_emu_run(const float* pts, const int* segs /*[nseg+1][4] incl.
   };
   emu::launch(cpp, kGgsThreads, body);
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// camera alignment (csrc/align.cuh): the two kernel bodies with the launch geometry of pdb_cameras_align
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" void cameras_align_emu(const float* Rs, const float* Ts, const float* Rt, const float* Tt, int count, int estimate_scale, float eps,
+                                  float* Ro, float* To, float* align) {
+  emu::launch(1, 32, [&]() { pdb::cameras_align_estimate_warp(Rs, Ts, Rt, Tt, count, estimate_scale, eps, align); });
+  emu::launch((count + 127) / 128, 128, [&]() { pdb::cameras_align_apply_thread(align, Rs, Ts, count, Ro, To); });
 }

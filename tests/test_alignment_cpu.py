@@ -121,3 +121,20 @@ def test_python_mirror_contract():
         pdb.corresponding_cameras_alignment(cams, cams, mode="other")
     with pytest.raises(_native.NativeError):
         pdb.corresponding_cameras_alignment(cams, cams)  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("n,noise,estimate_scale", [(1, 0.0, True), (2, 0.0, True), (20, 0.2, True), (20, 0.2, False), (80, 0.02, True), (200, 0.1, True)])
+def test_kernel_bodies_on_the_emulated_grid_match_oracle(n, noise, estimate_scale):
+    """The two kernels of pdb_cameras_align (one warp with shuffles for the estimate, 128-thread CTAs for the application) run on
+    the CPU emulation of the execution model (tests/host/cuda_emu.h) with the launch geometry of the C entry point."""
+    import __graft_entry__ as entry
+
+    lib = ctypes.CDLL(entry.build_emulator())
+    R_src, T_src, R_tgt, T_tgt, _ = similarity_scene(n, seed=300 + n, noise=noise)
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (R_src, T_src, R_tgt, T_tgt)]
+    Ro, To, al = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros(13, np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.cameras_align_emu(*[P(a) for a in arrs], n, int(estimate_scale), ctypes.c_float(1e-9), P(Ro), P(To), P(al))
+    want_R, want_T = oca.corresponding_cameras_alignment(*as_t(R_src, T_src, R_tgt, T_tgt), estimate_scale=estimate_scale)
+    np.testing.assert_allclose(Ro, want_R.numpy(), atol=1e-5)
+    np.testing.assert_allclose(To, want_T.numpy(), atol=3e-5 * max(1.0, np.abs(want_T.numpy()).max()))

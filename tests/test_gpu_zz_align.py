@@ -1,11 +1,10 @@
 """GPU test of pdb_cameras_align / posediffusion_b200.corresponding_cameras_alignment (demo.py:126-128).
 
-Written in a session without GPU access: the device maths is verified on the host (tests/test_alignment_cpu.py runs the same
-__host__ __device__ functions), the two kernels themselves have not run on a B200 yet, so this file only runs with
-PDB_TEST_EXPERIMENTAL=1 until it has been seen green.
+Written in a session without GPU access.  What was verified without a GPU: the device maths on the host (same __host__ __device__
+functions, tests/test_alignment_cpu.py), and the two kernel bodies on the CPU emulation of the execution model with the
+entry point's launch geometry (tests/host/cuda_emu.h).  The file sorts last among the GPU tests on purpose: it is the one
+test module whose kernels had not run on a B200 when it was committed.
 """
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -16,8 +15,7 @@ import posediffusion_b200 as pdb
 from posediffusion_b200 import metric
 from test_alignment_cpu import as_t, similarity_scene
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PDB_TEST_EXPERIMENTAL") != "1", reason="not yet run on a B200: set PDB_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n,noise,estimate_scale", [(1, 0.0, True), (2, 0.0, True), (5, 0.05, True), (20, 0.2, True), (20, 0.2, False), (80, 0.02, True)])

@@ -5,7 +5,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 #
 # Reading the results:
-#   exp_tests.log        gated GPU tests (tests/test_gpu_layout.py, tests/test_gpu_align.py) -- must be green before anything else
+#   exp_tests.log        gated GPU tests (tests/test_gpu_layout.py, tests/test_gpu_zz_align.py) -- must be green before anything else
 #   bench_*_{plain,paired}.json   bench.py lines; compare kernel_ms_per_loop.ggs and roofline.frac between the layouts
 #   probe_*_{plain,paired}.txt    per-stage cycles of the GGS iteration (stage1+2a is where the layout acts)
 #   ggs_*_paired.ncu-rep          ncu --set full of the paired kernel (issue slots busy / DRAM throughput vs profiles/r1_final_summary.md)
@@ -13,7 +13,7 @@ set -u
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
 export PDB_TEST_EXPERIMENTAL=1
-timeout 900 python -m pytest tests/test_gpu_layout.py tests/test_gpu_align.py -m gpu -q -x > gpurun_out/exp_tests.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_zz_align.py tests/test_gpu_layout.py -m gpu -q > gpurun_out/exp_tests.log 2>&1
 echo "experimental tests exit code $?" | tee -a gpurun_out/exp_tests.log
 for layout in plain paired; do
   timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --ggs-layout $layout > gpurun_out/bench_cfg3_$layout.json 2> gpurun_out/bench_cfg3_$layout.err
