@@ -108,7 +108,7 @@ PDB_HD void align_apply_camera(const float* al, const float* Rs, const float* Ts
   for (int c = 0; c < 3; ++c) To[c] = al[9] * Rs[0 + c] + al[10] * Rs[3 + c] + al[11] * Rs[6 + c] + al[12] * Ts[c];
 }
 
-// ---- kernel bodies (device side; csrc/api_post.cu wraps them in __global__ functions, tests/host/align_emu.cpp runs them on
+// ---- kernel bodies (device side; csrc/api_post.cu wraps them in __global__ functions, tests/host/kernels_emu.cpp runs them on
 // the CPU emulation of the execution model) ----
 // Estimate: ONE warp; lanes stride over the cameras, two passes (means, then centred second moments, as the reference computes
 // them), lane 0 finishes with the 3x3 SVD.  align[13] = {align_R (9, row-major), align_T (3), s}.

@@ -389,7 +389,11 @@ __device__ __forceinline__ void tail_token(const DenoiserDev& W, const DenoiserR
 template <int TS>
 __global__ void __launch_bounds__(kDenThreads, 1)
 denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R) {
+#ifdef PDB_EMU  // tests/host/cuda_emu.h (CPU emulation of this kernel, test harness only): dynamic shared memory of this CTA
+  float* const smem = reinterpret_cast<float*>(emu::g_cta->smem);
+#else
   extern __shared__ __align__(16) float smem[];
+#endif
   float* Xs = smem;  // [TS][K<=1024] or attention scratch
   __shared__ float pivot[32];
   const int S = R.tokens;

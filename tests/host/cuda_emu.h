@@ -1,5 +1,5 @@
 // TEST HARNESS (not product): a small CPU emulation of the CUDA execution model, enough to run the persistent
-// cooperative kernels of posediffusion_b200/csrc UNMODIFIED on the host (tests/host/ggs_emu.cpp compiles csrc/ggs.cuh with
+// cooperative kernels of posediffusion_b200/csrc UNMODIFIED on the host (tests/host/kernels_emu.cpp compiles csrc/ggs.cuh with
 // g++ through this header).  It exists so that kernel variants written without GPU access can still be executed -- warp
 // collectives, block barriers, shared memory, mbarrier / bulk-copy ring, grid-wide release / acquire barrier and all --
 // against the CPU oracle.  It says nothing about performance and nothing about memory-model races.

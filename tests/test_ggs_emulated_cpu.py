@@ -27,7 +27,7 @@ FLAGS = ((1, 1, 1), (0, 0, 1), (1, 0, 0), (0, 1, 0))
 def emu():
     import __graft_entry__ as entry
 
-    entry.build()  # the packer (layout image) lives in the product library, the emulated kernel in build/libggs_emu.so
+    entry.build()  # the packer (layout image) lives in the product library, the emulated kernel in build/libkernels_emu.so
     lib = C.CDLL(entry.build_emulator())
     lib.ggs_emu_run.restype = C.c_int
     return lib
