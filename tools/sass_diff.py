@@ -52,14 +52,22 @@ def main():
                 diff = sorted(k for k in a if k in b and a[k] != b[k])
                 gone = sorted(k for k in a if k not in b)
                 new = sorted(k for k in b if k not in a)
-                print(f"{obj}: {len(a)} kernels in {base}, {len(a) - len(diff) - len(gone)} identical, {len(diff)} changed, {len(gone)} renamed/removed, {len(new)} new")
+                # a kernel whose name changed (e.g. a new template parameter) but whose instruction stream did not
+                renamed = {k: next((n for n in new if b[n] == a[k]), None) for k in gone}
+                moved = sorted(k for k, n in renamed.items() if n)
+                gone = [k for k in gone if not renamed[k]]
+                new = [n for n in new if n not in renamed.values()]
+                print(f"{obj}: {len(a)} kernels in {base}: {len(a) - len(diff) - len(gone) - len(moved)} identical, {len(moved)} renamed but "
+                      f"identical, {len(diff)} changed, {len(gone)} removed; {len(new)} new")
+                for k in moved:
+                    print("   renamed, identical:", k[:110], "->", renamed[k][:110])
                 for k in diff:
                     print("   changed:", k[:140])
                 for k in gone:
-                    print("   renamed/removed:", k[:140])
+                    print("   removed:", k[:140])
                 for k in new:
                     print("   new:", k[:140])
-                changed += len(diff)
+                changed += len(diff) + len(gone)
             return 1 if changed else 0
         finally:
             subprocess.run(["git", "-C", ROOT, "worktree", "remove", "--force", tree])
