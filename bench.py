@@ -352,6 +352,18 @@ def main():
     for _ in range(max(3, args.warmup)):
         pose = one_loop()
     sync_all()
+    # both arms must run all 7 000 inner iterations per sequence (no early exit).  Checked once, outside the
+    # timed region, from the device-side statistics; recorded in the JSON line rather than asserted.
+    ggs_check = None
+    if per_pair:
+        try:
+            _, _, st = ctx.sample_loop(z_dev, draws_dev, problems, cfg, start_step, want_trail=False, want_stats=True)
+            rows = _native.stats_to_numpy(st)
+            ggs_check = {"inner_iterations_per_sequence": int(rows["iters"].sum()) // B, "early_exits": int(rows["dropped"].sum()),
+                         "expected": start_step * 7 * cfg["iter_num"]}
+        except Exception as exc:  # never let the check itself break the measurement
+            ggs_check = {"error": repr(exc)[:200]}
+        sync_all()
 
     # ---- timed region: K loops, L2 flushed between them, CUDA events on the launch stream ----
     ctx.profile(True)
@@ -424,6 +436,7 @@ def main():
         "clocks": clocks.summary(),
         "wall_s_timed_region": wall,
         "published_reference_note": "reference README.md:45 quotes ~60 s of sampling for a 20-frame GGS sequence on a Quadro GP100 (~1.7 steps/s, real hloc matches): other hardware, not this synthetic config, hence vs_baseline = null",
+        "ggs_iteration_check": ggs_check,
         "kernel_ms_per_loop": {"ggs": ggs_ms / args.steps, "denoiser": den_ms / args.steps, "ggs_launches": ggs_n // args.steps,
                                "denoiser_launches": den_n // args.steps},
     }
