@@ -131,3 +131,18 @@ def test_paired_layout_keeps_the_packed_fast_path_share_at_benchmark_shape(harne
         _, _, _, f_pair = _walk(harness, m, "paired", mode, 148)
         assert f_pair[0] >= f_plain[0]
         assert f_pair[0] >= floor * f_pair.sum()
+
+
+def test_layout_probe_rejects_bad_input():
+    m = syn.uniform_matches(3, 4, seed=0)
+    bad = dict(m)
+    bad["i12"] = m["i12"].copy()
+    bad["i12"][2, 0] = 3  # frame index outside [0, frames)
+    with pytest.raises(ValueError):
+        _native.pack_layout_host(bad, "plain")
+    with pytest.raises(KeyError):
+        _native.pack_layout_host(m, "transposed")
+    empty = {"kp1": np.zeros((0, 2)), "kp2": np.zeros((0, 2)), "i12": np.zeros((0, 2), np.int64), "img_shape": (4, 3, 224, 224)}
+    for layout in ("plain", "paired"):
+        segs, pts = _native.pack_layout_host(empty, layout)
+        assert segs.shape == (0, 4) and pts.shape == (0, 4)
