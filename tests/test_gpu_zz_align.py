@@ -40,5 +40,5 @@ def test_similarity_is_undone_and_are_vanishes():
     before = metric.compute_ARE(src.R, tgt.R).mean()
     aligned = pdb.corresponding_cameras_alignment(src, tgt)
     after = metric.compute_ARE(aligned.R, tgt.R).mean()
-    assert before > 5.0 and after < 0.05
+    assert before > 5.0 and after < 0.2  # acos near 1 turns one fp32 ulp of the trace into 0.02 degrees
     np.testing.assert_allclose(aligned.T.cpu().numpy(), T_tgt, atol=1e-4 * max(1.0, np.abs(T_tgt).max()))
