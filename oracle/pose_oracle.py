@@ -19,7 +19,7 @@ hat, HarmonicEmbedding; pytorch3d is a third-party dependency that is absent fro
 Pinning: the reference ships no tests or golden vectors for this path.
 The oracle is pinned instead against the reference's OWN modules imported from
 /root/reference in the build container (`oracle/make_golden.py` -> `tests/golden/*.npz`,
-`tests/test_oracle_vs_reference.py`).
+`tests/test_oracle_golden.py`).
 """
 from __future__ import annotations
 
