@@ -65,6 +65,9 @@ __device__ __forceinline__ int warp_reduce16_slot(int lane) {
 // ---------------------------------------------------------------------------------------------
 // Memory helpers, mbarrier + bulk asynchronous copy
 // ---------------------------------------------------------------------------------------------
+#if defined(PDB_EMU) && defined(__CUDACC__)
+#error "PDB_EMU is the CPU test harness of tests/host/cuda_emu.h; it must never be defined in an nvcc (product) build"
+#endif
 #ifdef PDB_EMU
 // TEST HARNESS ONLY (tests/host/cuda_emu.h): the inline-PTX helpers below restated for the CPU emulation that runs these
 // kernels unmodified on the host.  Never defined in a product build (nvcc does not see PDB_EMU).
