@@ -4,6 +4,8 @@
 // (csrc/align.cuh).  Build:  g++ -O1 -std=c++17 -shared -fPIC (see __graft_entry__.py::build_emulator).
 #include "cuda_emu.h"
 
+#include <chrono>
+
 #include "../../posediffusion_b200/csrc/ggs.cuh"
 #include "../../posediffusion_b200/csrc/align.cuh"
 #include "../../posediffusion_b200/csrc/denoiser.cuh"
@@ -56,7 +58,18 @@ static void run_cta(int block_index, int grid, int block, const std::function<vo
     cta.ctx[t].uc_link = &cta.sched;
     makecontext(&cta.ctx[t], trampoline, 0);
   }
+  // watchdog: a kernel that deadlocks (a barrier some threads never reach, an mbarrier phase that never completes) must fail
+  // the test run instead of hanging it
+  const char* limit_env = getenv("PDB_EMU_TIMEOUT_S");
+  const double limit_s = limit_env ? atof(limit_env) : 900.0;
+  const auto t_start = std::chrono::steady_clock::now();
+  unsigned long passes = 0;
   while (cta.live > 0) {
+    if ((++passes & 1023) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > limit_s) {
+      fprintf(stderr, "emu: CTA %d made no end after %.0f s (%d of %d threads alive, block barrier %d/%d arrived): deadlock?\n",
+              block_index, limit_s, cta.live, block, cta.block_count, cta.live);
+      abort();
+    }
     for (int t = 0; t < block; ++t) {
       if (cta.done[t]) continue;
       cta.current = t;
