@@ -36,6 +36,8 @@ WORKLOADS = {
     "cfg3": (20, 2048, "BASELINE configs[2]: 1 sequence x 20 frames per GPU, T=100, GGS on (start_step 10, 700 inner iters/step), "
                       "M=2048 uniform-random matches for each of the 380 ordered pairs (778240 matches)"),
     "cfg2": (20, 0, "BASELINE configs[1]: 1 sequence x 20 frames per GPU, T=100, GGS off (denoiser-only path)"),
+    "cfg4": (20, 2048, "BASELINE configs[3]: 64 sequences x 20 frames sharded over 8 GPUs = 8 sequences per GPU (--seqs-per-gpu defaults to 8 "
+                      "here), T=100, GGS on, 778240 matches per sequence; one GGS launch optimises the GPU's 8 sequences side by side"),
     "cfg5": (80, 4096, "BASELINE configs[4]: 1 sequence x 80 frames, T=100, GGS on, M=4096 x 6320 ordered pairs (25886720 matches)"),
 }
 FEATURES_DESC = ("widened row SURVEY 8f-2 (NOT the headline): MultiScaleImageFeatureExtractor = DINO ViT-S/16 at scales 1, 1/2, 1/3 over "
@@ -268,7 +270,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["features"])
-    ap.add_argument("--seqs-per-gpu", type=int, default=1)
+    ap.add_argument("--seqs-per-gpu", type=int, default=None, help="sequences per GPU (default 1; 8 for --workload cfg4)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU GGS iterations in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -277,6 +279,8 @@ def main():
     ap.add_argument("--denoiser-engine", default="auto", choices=["auto", "fp32", "tf32"],
                     help="auto = exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tiles (TF32) at or above")
     args = ap.parse_args()
+    if args.seqs_per_gpu is None:
+        args.seqs_per_gpu = 8 if args.workload == "cfg4" else 1
     if args.workload == "features":
         return features_main(args)
     frames, per_pair, desc = WORKLOADS[args.workload]
