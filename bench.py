@@ -461,8 +461,9 @@ def main():
             "note": ("algorithmic bytes = 16 B x matches x inner iterations; at this size the CTA slices of the match set (12.45 MB total) "
                      "stay resident in shared memory for the whole launch, so DRAM traffic is ~0.2% of the algorithmic bytes by design "
                      "and the iteration is latency-chain bound (run --workload cfg5 for the HBM-streaming case: 414 MB per inner iteration)")
-                    if args.workload == "cfg3" else
-                    "algorithmic bytes = 16 B x matches x inner iterations, streamed from HBM every inner iteration through the TMA unit",
+                    if (args.workload == "cfg3" and B == 1) else
+                    "algorithmic bytes = 16 B x matches x inner iterations, streamed every inner iteration through the TMA unit's bulk-async "
+                    "ring (from HBM at config 5: 414 MB per iteration; largely from L2 when the sequences' match sets fit its 126 MB)",
         }
     if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only
         threads = min(os.cpu_count() or 1, 32)
