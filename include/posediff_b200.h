@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PDB_ABI_VERSION 1
+#define PDB_ABI_VERSION 2
 
 typedef enum pdb_status {
   PDB_OK = 0,
@@ -154,6 +154,7 @@ int pdb_matches_info(const pdb_matches* m, int64_t* m_total, int32_t* segments, 
  * that the 128-bit loads are directly the operand pairs of the packed fp32x2 pipe).  Same 16 B per match, same results;
  * the environment variable PDB_GGS_LAYOUT=paired selects 1 at pdb_create.  EXPERIMENTAL until measured on a B200. */
 int pdb_ggs_layout(pdb_context* ctx, int32_t layout);
+int pdb_ggs_layout_get(const pdb_context* ctx); /* the layout new match sets are packed in (0 / 1) */
 
 /* Host-only layout probe (no GPU, no context; test infrastructure): writes the stream image pdb_matches_pack would upload
  * for reference-format matches -- segs_out [*nseg][4] = {first_round, count, frame_a, frame_b}, pts_out [*rounds * 32 * 4]
@@ -178,16 +179,18 @@ int pdb_ggs(pdb_context* ctx, pdb_matches* const* problems, int32_t batch, float
 /* ---- sampler ------------------------------------------------------------------------------------
  * p_sample_loop: draws_dev[T+1, B, N, 9] holds the Gaussian draws in the reference's order (draws[0] = x_T,
  * draws[1+k] = noise of loop iteration k, i.e. t = T-1-k; unused on guided steps and at t = 0).
- * problems == NULL -> no guidance.  cond_start_step as in p_sample (:270).  trail_dev may be NULL, else
+ * problems == NULL -> no guidance; otherwise problems[n_problems] holds ONE match set per sequence: n_problems must equal
+ * `batch` and every set must have been packed for `frames` frames (PDB_ERR_INVALID otherwise -- the kernels index
+ * problems[b] and stride the pose by the set's frame count).  cond_start_step as in p_sample (:270).  trail_dev may be NULL, else
  * [T+1, B, N, 9].  stats_dev may be NULL, else [cond_start_step, batch] records (row 0 = first guided step). */
 int pdb_sample_loop(pdb_context* ctx, const float* z_dev, const float* draws_dev, int32_t batch, int32_t frames,
-                    pdb_matches* const* problems, const pdb_ggs_config* cfg, int32_t cond_start_step,
-                    float* pose_dev, float* trail_dev, pdb_ggs_stats* stats_dev, void* stream);
+                    pdb_matches* const* problems, int32_t n_problems, const pdb_ggs_config* cfg,
+                    int32_t cond_start_step, float* pose_dev, float* trail_dev, pdb_ggs_stats* stats_dev, void* stream);
 
 /* The same with host buffers (pinned or pageable): copies z and the draws in, runs, copies pose (and the
  * optional trajectory / stats) out, synchronises the stream.  This is the end-to-end call bench.py times. */
 int pdb_sample_loop_host(pdb_context* ctx, const float* z_host, const float* draws_host, int32_t batch,
-                         int32_t frames, pdb_matches* const* problems, const pdb_ggs_config* cfg,
+                         int32_t frames, pdb_matches* const* problems, int32_t n_problems, const pdb_ggs_config* cfg,
                          int32_t cond_start_step, float* pose_host, float* trail_host, pdb_ggs_stats* stats_host,
                          void* stream);
 

@@ -260,3 +260,117 @@ def sampson_closed_form_f64(pose, matches: Dict, update_R=True, update_T=True, u
         out["loss"] = float("nan")
         out["grad"] = np.full((frames, 9), np.nan)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Same closed form, vectorised for BASELINE-size match sets (778 240 / 25 886 720 rows)
+# ---------------------------------------------------------------------------------------------
+def sampson_closed_form_f64_large(pose, matches: Dict, update_R=True, update_T=True, update_FL=True, sampson_max=10.0,
+                                  chunk_rows: int = 1 << 20):
+    """`sampson_closed_form_f64` for pair-contiguous match sets of any size: identical maths (stage 1 per match in float64
+    on the float32-rounded coordinates, stage 2 per pair segment), evaluated in row chunks with `np.add.reduceat` over the
+    maximal runs of equal (i12[:,0], i12[:,1]) instead of one boolean mask per pair.  Returns dict(loss, n_valid, logged,
+    grad [N,9]); additionally `band`: the number of matches whose error lies within 1e-5 (relative) of the threshold,
+    i.e. the matches whose validity an fp32 evaluation may legitimately flip."""
+    frames, _, height, width = matches["img_shape"]
+    pose = np.asarray(pose, dtype=np.float64).reshape(frames, 9)
+    Rp, Rcv, tcv, A, fl, in_range, fpx, Kinv, scale = frame_terms(pose, height, width)
+    ia = np.asarray(matches["i12"][:, 0], dtype=np.int64)
+    ib = np.asarray(matches["i12"][:, 1], dtype=np.int64)
+    total = len(ia)
+    pair = ia * frames + ib
+    # maximal runs of equal pair index (the segments of the device layout)
+    starts = np.flatnonzero(np.concatenate([[True], pair[1:] != pair[:-1]])) if total else np.zeros(0, np.int64)
+    seg_pair = pair[starts] if total else np.zeros(0, np.int64)
+    # F' of every pair that occurs
+    uniq = np.unique(seg_pair)
+    F_of = {}
+    for pid in uniq:
+        a, b = divmod(int(pid), frames)
+        F_of[int(pid)] = pair_F(Rcv, A, Kinv, a, b)
+    F_seg = np.stack([F_of[int(p)] for p in seg_pair]) if len(seg_pair) else np.zeros((0, 3, 3))
+    G_seg = np.zeros((len(starts), 3, 3))
+    n_valid = 0
+    band = 0
+    clamp_sum = 0.0
+    loss_sum = 0.0
+    seg_of_row_start = np.searchsorted(starts, np.arange(0, total, chunk_rows), side="right") - 1 if total else []
+    for ci, r0 in enumerate(range(0, total, chunk_rows)):
+        r1 = min(total, r0 + chunk_rows)
+        s0 = int(seg_of_row_start[ci])
+        s1 = int(np.searchsorted(starts, r1 - 1, side="right"))  # segments [s0, s1) intersect the chunk
+        local_starts = np.maximum(starts[s0:s1], r0) - r0
+        seg_id = np.repeat(np.arange(s0, s1), np.diff(np.concatenate([local_starts, [r1 - r0]])))
+        kp1 = np.asarray(matches["kp1"][r0:r1], dtype=np.float32).astype(np.float64)
+        kp2 = np.asarray(matches["kp2"][r0:r1], dtype=np.float32).astype(np.float64)
+        n = r1 - r0
+        x1 = np.concatenate([kp1, np.ones((n, 1))], 1)
+        x2 = np.concatenate([kp2, np.ones((n, 1))], 1)
+        Fm = F_seg[seg_id]                                   # [n,3,3]
+        left = np.einsum("mi,mij->mj", x1, Fm)
+        right = np.einsum("mij,mj->mi", Fm, x2)
+        top = (left * x2).sum(1)
+        bottom = left[:, 0] ** 2 + left[:, 1] ** 2 + right[:, 0] ** 2 + right[:, 1] ** 2
+        with np.errstate(invalid="ignore", divide="ignore"):
+            err = top**2 / bottom
+            keep = err < sampson_max
+            band += int((np.abs(err - sampson_max) <= 1e-5 * sampson_max).sum())
+            clamp_sum += np.where(err > sampson_max, sampson_max, err).sum()
+            n_valid += int(keep.sum())
+            loss_sum += err[keep].sum()
+            wgt = keep.astype(np.float64)
+            ca = wgt * (2 * top / bottom)
+            cb = wgt * (2 * err / bottom)
+            lz = left.copy()
+            lz[:, 2] = 0
+            rz = right.copy()
+            rz[:, 2] = 0
+            # G_ij = sum ca x1_i x2_j - cb x1_i lz_j - cb rz_i x2_j   per match, then summed per segment
+            w = ca[:, None] * x2 - cb[:, None] * lz          # [n,3]
+            per = x1[:, :, None] * w[:, None, :] - (cb[:, None] * rz)[:, :, None] * x2[:, None, :]
+            G_seg[s0:s1] += np.add.reduceat(per.reshape(n, 9), local_starts, axis=0).reshape(-1, 3, 3)
+    # ---- stage 2: adjoint of pose -> F' (as above) ----
+    gR = np.zeros((frames, 3, 3))
+    gA = np.zeros((frames, 3, 3))
+    gK = np.zeros((3, 3))
+    for s, pid in enumerate(seg_pair):
+        a, b = divmod(int(pid), frames)
+        Gp = G_seg[s]
+        M = pair_M(Rcv, A, a, b)
+        H = Kinv @ Gp @ Kinv.T
+        gK += M @ Kinv @ Gp.T + M.T @ Kinv @ Gp
+        gA[a] += -H @ Rcv[b]
+        gR[b] += -H.T @ A[a]
+        gR[a] += -H @ A[b]
+        gA[b] += -H.T @ Rcv[a]
+    grad = np.zeros((frames, 9))
+    D = np.diag([-1.0, -1.0, 1.0])
+    g_fpx = np.array([(-gK[0, 0] + (width / 2.0) * gK[0, 2]) / fpx[0] ** 2, (-gK[1, 1] + (height / 2.0) * gK[1, 2]) / fpx[1] ** 2])
+    for i in range(frames):
+        gRcv = gR[i] - _hat_np(tcv[i]) @ gA[i]
+        Wm = gA[i] @ Rcv[i].T
+        gt = np.array([Wm[2, 1] - Wm[1, 2], Wm[0, 2] - Wm[2, 0], Wm[1, 0] - Wm[0, 1]])
+        if update_T:
+            grad[i, :3] = D @ gt
+        if update_R:
+            gRp = (D @ gRcv).T
+            w, x, y, z = pose[i, 3:7]
+            q = np.array([w, x, y, z])
+            s2 = 2.0 / (q @ q)
+            B = np.array([[-(y * y + z * z), x * y - z * w, x * z + y * w], [x * y + z * w, -(x * x + z * z), y * z - x * w],
+                          [x * z - y * w, y * z + x * w, -(x * x + y * y)]])
+            dB = [np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]]), np.array([[0, y, z], [y, -2 * x, -w], [z, w, -2 * x]]),
+                  np.array([[-2 * y, x, w], [x, 0, z], [-w, z, -2 * y]]), np.array([[-2 * z, -w, x], [w, -2 * z, y], [x, y, 0]])]
+            gB = (gRp * B).sum()
+            for k in range(4):
+                grad[i, 3 + k] = -s2 * s2 * q[k] * gB + s2 * (gRp * dB[k]).sum()
+        if update_FL:
+            grad[i, 7:9] = g_fpx * scale / frames * fl[i] * in_range[i]
+    out = {"n_valid": n_valid, "band": band, "logged": clamp_sum / total if total else float("nan")}
+    if n_valid > 0:
+        out["loss"] = loss_sum / n_valid
+        out["grad"] = grad / n_valid
+    else:
+        out["loss"] = float("nan")
+        out["grad"] = np.full((frames, 9), np.nan)
+    return out

@@ -9,11 +9,11 @@ from .camera_alignment import corresponding_cameras_alignment
 from .camera_transform import PerspectiveCameras, pose_encoding_to_camera
 from .denoiser import Denoiser, TransformerEncoderWrapper
 from .gaussian_diffuser import GaussianDiffusion
-from .geometry_guided_sampling import geometry_guided_sampling
+from .geometry_guided_sampling import geometry_guided_sampling, invalidate_matches
 from .image_feature_extractor import MultiScaleImageFeatureExtractor
 from .pose_diffusion_model import PoseDiffusionModel
 
 __all__ = [
     "PoseDiffusionModel", "GaussianDiffusion", "Denoiser", "TransformerEncoderWrapper", "MultiScaleImageFeatureExtractor",
-    "geometry_guided_sampling", "pose_encoding_to_camera", "PerspectiveCameras", "corresponding_cameras_alignment",
+    "geometry_guided_sampling", "invalidate_matches", "pose_encoding_to_camera", "PerspectiveCameras", "corresponding_cameras_alignment",
 ]

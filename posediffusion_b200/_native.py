@@ -79,11 +79,12 @@ EXPORTS = {
     "pdb_matches_free": (None, [C.c_void_p]),
     "pdb_matches_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "pdb_ggs_layout": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pdb_ggs_layout_get": (C.c_int, [C.c_void_p]),
     "pdb_debug_pack_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                         C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "pdb_sampson_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_ggs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(GgsConfig), C.c_void_p, C.c_void_p]),
-    "pdb_sample_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_sample_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_pose_to_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_rel_pose_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdb_cameras_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double,
@@ -92,7 +93,7 @@ EXPORTS = {
     "pdb_vit_pos_table": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "pdb_extract_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pdb_extract_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p]),
-    "pdb_sample_loop_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_sample_loop_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -114,6 +115,9 @@ def load_library() -> C.CDLL:
                 fn = getattr(lib, name)  # AttributeError if the symbol is not exported
                 fn.restype = res
                 fn.argtypes = args
+            if lib.pdb_abi_version() != PDB_ABI_VERSION:
+                raise NativeError(f"{LIB_PATH} has ABI version {lib.pdb_abi_version()}, this binding expects {PDB_ABI_VERSION}: "
+                                  "rebuild with `python -m posediffusion_b200.build --force`")
             _lib = lib
     return _lib
 
@@ -138,6 +142,8 @@ def vit_pos_table(pos_embed: np.ndarray, grid_h: int, grid_w: int) -> np.ndarray
 
 
 GGS_LAYOUTS = {"plain": 0, "paired": 1}
+PDB_ABI_VERSION = 2  # include/posediff_b200.h
+PDB_OK, PDB_ERR_INVALID, PDB_ERR_CUDA, PDB_ERR_STATE, PDB_ERR_LIMIT = 0, -1, -2, -3, -4
 
 
 def pack_layout_host(matches_dict: Dict, layout: str = "plain"):
@@ -223,6 +229,7 @@ class Context:
             raise NativeError(f"pdb_create({device_index}) failed: {self.lib.pdb_last_error(None).decode()}")
         self.handle = handle
         self.weights_key = None
+        self.ggs_layout = {v: k for k, v in GGS_LAYOUTS.items()}[int(self.lib.pdb_ggs_layout_get(handle))]
 
     @classmethod
     def get(cls, device) -> "Context":
@@ -263,6 +270,7 @@ class Context:
     def set_ggs_layout(self, layout: str = "plain"):
         """Stream layout of match sets packed from now on: 'plain' (default) or 'paired' (csrc/ggs_layout.cuh; experimental)."""
         self._ok(self.lib.pdb_ggs_layout(self.handle, GGS_LAYOUTS[layout]), "pdb_ggs_layout")
+        self.ggs_layout = layout
 
     def tc_linear(self, x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, relu: bool = False) -> torch.Tensor:
         """Y = relu?(x @ w^T + bias + residual) on the tcgen05 tensor cores (TF32 products, fp32 accumulate)."""
@@ -440,6 +448,15 @@ class Context:
     def _problem_array(self, problems: Sequence[Matches]):
         return (C.c_void_p * len(problems))(*[p.handle for p in problems])
 
+    @staticmethod
+    def _check_problems(problems: Sequence[Matches], batch: int, frames: int):
+        """One match set per sequence, each packed for the pose's frame count (the library checks the same)."""
+        if len(problems) != batch:
+            raise ValueError(f"{len(problems)} match sets for a batch of {batch} sequences")
+        for i, p in enumerate(problems):
+            if p.frames != frames:
+                raise ValueError(f"match set {i} has img_shape[0] = {p.frames}, the sequence has {frames} frames")
+
     def ggs(self, problems: Sequence[Matches], pose: torch.Tensor, cfg: Dict, want_stats: bool = True):
         """In-place geometry-guided sampling on pose [B, N, 9]; returns a device stats tensor (uint8 view) or None."""
         B = len(problems)
@@ -458,12 +475,14 @@ class Context:
         pose = torch.empty(B, N, TARGET_DIM, device=self.device)
         trail = torch.empty(NUM_TIMESTEPS + 1, B, N, TARGET_DIM, device=self.device) if want_trail else None
         guided = max(0, min(int(cond_start_step), NUM_TIMESTEPS)) if problems else 0
+        if problems:
+            self._check_problems(problems, B, N)
         stats = None
         if want_stats and guided:
             stats = torch.zeros(guided * B * GGS_STATS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
         conf = ggs_config_struct(cfg) if problems else None
         self._ok(self.lib.pdb_sample_loop(self.handle, z.data_ptr(), draws.data_ptr(), B, N,
-                                          self._problem_array(problems) if problems else None,
+                                          self._problem_array(problems) if problems else None, len(problems) if problems else 0,
                                           C.byref(conf) if conf is not None else None, int(cond_start_step), pose.data_ptr(),
                                           trail.data_ptr() if want_trail else None,
                                           stats.data_ptr() if stats is not None else None, _stream_ptr(self.device)),
@@ -474,10 +493,13 @@ class Context:
                          pose_out: np.ndarray, trail_out: Optional[np.ndarray] = None, stats_out: Optional[np.ndarray] = None):
         """Host-buffer entry (numpy float32 arrays, ideally pinned): the end-to-end call bench.py times."""
         B, N, _ = z.shape
+        if problems:
+            self._check_problems(problems, B, N)
         conf = ggs_config_struct(cfg) if problems else None
         with torch.cuda.device(self.device):
             self._ok(self.lib.pdb_sample_loop_host(self.handle, z.ctypes.data, draws.ctypes.data, B, N,
                                                    self._problem_array(problems) if problems else None,
+                                                   len(problems) if problems else 0,
                                                    C.byref(conf) if conf is not None else None, int(cond_start_step),
                                                    pose_out.ctypes.data, trail_out.ctypes.data if trail_out is not None else None,
                                                    stats_out.ctypes.data if stats_out is not None else None,

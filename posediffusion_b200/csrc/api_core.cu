@@ -389,6 +389,8 @@ int pdb_ggs_layout(pdb_context* c, int32_t layout) {
   return PDB_OK;
 }
 
+int pdb_ggs_layout_get(const pdb_context* c) { return c ? reinterpret_cast<const Context*>(c)->ggs_layout : -1; }
+
 // Host-only probe of the stream layout (no GPU, no context): lays reference-format matches out exactly as pdb_matches_pack
 // would place them in HBM.  The CPU tests walk this image with the kernel's own partition functions (ggs_layout.cuh).
 int pdb_debug_pack_layout(const double* kp1, const double* kp2, const int64_t* i12, int64_t m_total, int32_t frames, int32_t layout,
@@ -479,20 +481,32 @@ int launch_ggs_layout(Context* ctx, int layout, const GgsBatch& batch, int nprob
 
 namespace pdb {
 
-// Enqueue geometry-guided sampling for `batch` sequences (pose_dev [batch, N, 9] updated in place).
-int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* pose_dev, const pdb_ggs_config* cfg,
-                pdb_ggs_stats* stats_dev, cudaStream_t st) {
-  if (batch < 1 || !problems || !pose_dev || !cfg) return ctx->fail(PDB_ERR_INVALID, "bad GGS arguments");
-  if (cfg->iter_num < 0) return ctx->fail(PDB_ERR_INVALID, "iter_num < 0");
-  int max_frames = 0;
-  size_t ws_need = 0;
+// One match set per sequence, all packed for `frames` frames (the pose stride of pose_dev [batch, frames, 9]) and in one
+// stream layout.  frames <= 0: take the frame count of the first set (pdb_ggs, whose pose shape is defined by the sets).
+int check_ggs_problems(Context* ctx, pdb_matches* const* problems, int batch, int frames) {
+  if (batch < 1 || !problems) return ctx->fail(PDB_ERR_INVALID, "bad GGS arguments");
   for (int b = 0; b < batch; ++b) {
     if (!problems[b]) return ctx->fail(PDB_ERR_INVALID, "null match set %d", b);
     const Matches* m = reinterpret_cast<const Matches*>(problems[b]);
-    if (m->frames != reinterpret_cast<const Matches*>(problems[0])->frames)
-      return ctx->fail(PDB_ERR_INVALID, "all sequences of a batch must have the same frame count");
+    if (frames <= 0) frames = m->frames;
+    if (m->frames != frames)
+      return ctx->fail(PDB_ERR_INVALID, "match set %d was packed for %d frames (img_shape[0]), the pose has %d", b, m->frames, frames);
     if (m->layout != reinterpret_cast<const Matches*>(problems[0])->layout)
       return ctx->fail(PDB_ERR_INVALID, "all match sets of a batch must use the same stream layout (pdb_ggs_layout)");
+  }
+  return PDB_OK;
+}
+
+// Enqueue geometry-guided sampling for `batch` sequences (pose_dev [batch, frames, 9] updated in place).
+int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frames, float* pose_dev, const pdb_ggs_config* cfg,
+                pdb_ggs_stats* stats_dev, cudaStream_t st) {
+  if (batch < 1 || !problems || !pose_dev || !cfg) return ctx->fail(PDB_ERR_INVALID, "bad GGS arguments");
+  if (cfg->iter_num < 0) return ctx->fail(PDB_ERR_INVALID, "iter_num < 0");
+  if (int rc = check_ggs_problems(ctx, problems, batch, frames)) return rc;
+  int max_frames = 0;
+  size_t ws_need = 0;
+  for (int b = 0; b < batch; ++b) {
+    const Matches* m = reinterpret_cast<const Matches*>(problems[b]);
     max_frames = max_frames > m->frames ? max_frames : m->frames;
     ws_need += ggs_ws_per_problem(m->frames);
   }
@@ -553,7 +567,7 @@ int pdb_ggs(pdb_context* c, pdb_matches* const* problems, int32_t batch, float* 
   if (!c) return PDB_ERR_INVALID;
   Context* ctx = reinterpret_cast<Context*>(c);
   PDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  return enqueue_ggs(ctx, problems, batch, pose_dev, cfg, stats_dev, static_cast<cudaStream_t>(stream));
+  return enqueue_ggs(ctx, problems, batch, 0, pose_dev, cfg, stats_dev, static_cast<cudaStream_t>(stream));
 }
 
 int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_dev, int32_t update_R, int32_t update_T,

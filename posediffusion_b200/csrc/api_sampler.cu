@@ -12,8 +12,9 @@
 using namespace pdb;
 
 namespace pdb {
-int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, float* pose_dev, const pdb_ggs_config* cfg,
+int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frames, float* pose_dev, const pdb_ggs_config* cfg,
                 pdb_ggs_stats* stats_dev, cudaStream_t st);
+int check_ggs_problems(Context* ctx, pdb_matches* const* problems, int batch, int frames);
 
 int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st);
 void vit_release(Context* ctx);
@@ -442,12 +443,16 @@ int pdb_p_sample(pdb_context* c, const float* x_dev, int32_t t, const float* z_d
 }
 
 int pdb_sample_loop(pdb_context* c, const float* z_dev, const float* draws_dev, int32_t batch, int32_t frames,
-                    pdb_matches* const* problems, const pdb_ggs_config* cfg, int32_t cond_start_step, float* pose_dev,
-                    float* trail_dev, pdb_ggs_stats* stats_dev, void* stream) {
+                    pdb_matches* const* problems, int32_t n_problems, const pdb_ggs_config* cfg, int32_t cond_start_step,
+                    float* pose_dev, float* trail_dev, pdb_ggs_stats* stats_dev, void* stream) {
   if (!c) return PDB_ERR_INVALID;
   Context* ctx = reinterpret_cast<Context*>(c);
   if (!z_dev || !draws_dev || !pose_dev) return ctx->fail(PDB_ERR_INVALID, "null argument");
   if (problems && !cfg) return ctx->fail(PDB_ERR_INVALID, "GGS config missing");
+  if (problems && n_problems != batch)
+    return ctx->fail(PDB_ERR_INVALID, "%d match sets for a batch of %d sequences (one per sequence)", n_problems, batch);
+  if (problems)  // before anything is enqueued: a set packed for another frame count would stride the pose wrongly
+    if (int rc = check_ggs_problems(ctx, problems, batch, frames)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PDB_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t n = (size_t)batch * frames * kTargetDim;
@@ -474,7 +479,7 @@ int pdb_sample_loop(pdb_context* c, const float* z_dev, const float* draws_dev, 
     first = false;
     if (int rc = enqueue_denoiser(ctx, run, st)) return rc;
     pdb_ggs_stats* stats = stats_dev ? stats_dev + (size_t)(guide_below - 1 - t) * batch : nullptr;
-    if (int rc = enqueue_ggs(ctx, problems, batch, pose_dev, cfg, stats, st)) return rc;
+    if (int rc = enqueue_ggs(ctx, problems, batch, frames, pose_dev, cfg, stats, st)) return rc;
     if (trail_dev)
       PDB_CUDA(ctx, cudaMemcpyAsync(trail_dev + (size_t)(kT - t) * n, pose_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   }
@@ -482,11 +487,13 @@ int pdb_sample_loop(pdb_context* c, const float* z_dev, const float* draws_dev, 
 }
 
 int pdb_sample_loop_host(pdb_context* c, const float* z_host, const float* draws_host, int32_t batch, int32_t frames,
-                         pdb_matches* const* problems, const pdb_ggs_config* cfg, int32_t cond_start_step,
+                         pdb_matches* const* problems, int32_t n_problems, const pdb_ggs_config* cfg, int32_t cond_start_step,
                          float* pose_host, float* trail_host, pdb_ggs_stats* stats_host, void* stream) {
   if (!c) return PDB_ERR_INVALID;
   Context* ctx = reinterpret_cast<Context*>(c);
   if (!z_host || !draws_host || !pose_host) return ctx->fail(PDB_ERR_INVALID, "null argument");
+  if (problems && n_problems != batch)
+    return ctx->fail(PDB_ERR_INVALID, "%d match sets for a batch of %d sequences (one per sequence)", n_problems, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PDB_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t S = (size_t)batch * frames, n = S * kTargetDim;
@@ -504,7 +511,7 @@ int pdb_sample_loop_host(pdb_context* c, const float* z_host, const float* draws
   PDB_CUDA(ctx, cudaMemcpyAsync(z_dev, z_host, sizeof(float) * f_z, cudaMemcpyHostToDevice, st));
   PDB_CUDA(ctx, cudaMemcpyAsync(draws_dev, draws_host, sizeof(float) * f_draws, cudaMemcpyHostToDevice, st));
   if (stats_dev) PDB_CUDA(ctx, cudaMemsetAsync(stats_dev, 0, stats_bytes, st));
-  if (int rc = pdb_sample_loop(c, z_dev, draws_dev, batch, frames, problems, cfg, cond_start_step, pose_dev, trail_dev,
+  if (int rc = pdb_sample_loop(c, z_dev, draws_dev, batch, frames, problems, n_problems, cfg, cond_start_step, pose_dev, trail_dev,
                                stats_dev, stream))
     return rc;
   PDB_CUDA(ctx, cudaMemcpyAsync(pose_host, pose_dev, sizeof(float) * f_pose, cudaMemcpyDeviceToHost, st));

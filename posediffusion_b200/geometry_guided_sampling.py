@@ -7,34 +7,58 @@ running all five GGS_optimize phases in one persistent sm_100a kernel launch.
 `matches_dict` is the reference's dict (kp1/kp2 float64 [M,2], i12 int64 [M,2], img_shape); for a batch of
 B > 1 sequences pass a list of B such dicts (the reference's own GGS is only meaningful for B = 1,
 SURVEY.md §0 row 5).  Matches are packed and uploaded ONCE per dict (the reference re-uploads 48 B/match
-on every guided step, :19-24) and cached on the dict object.
+on every guided step, :19-24) and cached per dict object, keyed on the identity of its arrays plus a sampled content
+fingerprint; `invalidate_matches(d)` drops the device copy after an in-place edit.
 """
 from __future__ import annotations
 
-import weakref
+from collections import OrderedDict
 from typing import Dict, List, Sequence, Union
 
+import numpy as np
 import torch
 
 from . import _native
 
-_KEEP: Dict[int, tuple] = {}
+_KEEP: "OrderedDict[int, tuple]" = OrderedDict()
+_KEEP_MAX = 8  # packed sets pinned on the GPU at most (least recently used goes first)
+
+
+def _fingerprint(a) -> tuple:
+    """Cheap content tag of a match array: shape, dtype and 64 strided samples (a full checksum of a 778 240-row set costs
+    more than packing it).  Catches a different set behind a recycled object id and most in-place edits; call
+    `invalidate_matches` after editing `kp1` / `kp2` / `i12` in place to be certain."""
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 64)
+    return (a.shape, a.dtype.str, flat[::step][:64].tobytes(), flat[-1:].tobytes())
+
+
+def invalidate_matches(matches_dict: Union[Dict, Sequence[Dict], None] = None) -> None:
+    """Forget the device copy of `matches_dict` (all cached sets if None): the next call packs and uploads it again, as the
+    reference does on every call (util/geometry_guided_sampling.py:19-24)."""
+    if matches_dict is None:
+        _KEEP.clear()
+        return
+    for d in ([matches_dict] if isinstance(matches_dict, dict) else list(matches_dict)):
+        _KEEP.pop(id(d), None)
 
 
 def packed_matches(ctx: "_native.Context", matches_dict: Union[Dict, Sequence[Dict]]) -> List["_native.Matches"]:
     dicts = [matches_dict] if isinstance(matches_dict, dict) else list(matches_dict)
     out = []
     for d in dicts:
-        key = (id(d), ctx.device.index, id(d["kp1"]), id(d["kp2"]), id(d["i12"]), tuple(d["img_shape"]))
+        arrays = (d["kp1"], d["kp2"], d["i12"])
+        key = (ctx.device.index, ctx.ggs_layout, tuple(id(a) for a in arrays), tuple(d["img_shape"]),
+               tuple(_fingerprint(a) for a in arrays))
         hit = _KEEP.get(id(d))
         if hit is None or hit[0] != key:
-            hit = (key, ctx.pack_matches(d))
+            # the entry holds the source arrays: their ids cannot be recycled for other data while it is cached
+            hit = (key, ctx.pack_matches(d), arrays)
             _KEEP[id(d)] = hit
-            try:  # drop the cache entry when the dict goes away (plain dicts are not weak-referenceable)
-                weakref.finalize(d, _KEEP.pop, id(d), None)
-            except TypeError:
-                if len(_KEEP) > 64:
-                    _KEEP.pop(next(iter(_KEEP)))
+            while len(_KEEP) > _KEEP_MAX:
+                _KEEP.popitem(last=False)
+        _KEEP.move_to_end(id(d))
         out.append(hit[1])
     return out
 

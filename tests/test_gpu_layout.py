@@ -1,13 +1,8 @@
-"""GPU parity tests of the EXPERIMENTAL paired match-stream layout (csrc/ggs_layout.cuh, `pdb_ggs_layout(ctx, 1)`).
+"""GPU parity tests of the paired match-stream layout (csrc/ggs_layout.cuh, `pdb_ggs_layout(ctx, 1)`).
 
-The layout was written in a session without GPU access: its indexing contract is covered on the CPU
-(tests/test_layout_cpu.py), the default (plain) instantiations of the kernel are SASS-identical to the measured build,
-but the paired kernels have not run on a B200 yet.  These tests therefore only run with PDB_TEST_EXPERIMENTAL=1
-(`PDB_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_layout.py -m gpu`); the default stays `plain` until they are
-green and the layout is measured.
-
-Same tolerances as tests/test_gpu_parity.py; against the plain layout the statistics must agree exactly (valid counts)
-or up to summation order (sums).
+Every kernel instantiation the library ships runs here on the device (`ggs_entry<*, true>` as well as `<*, false>`):
+the same fixtures and tolerances as tests/test_gpu_parity.py; against the plain layout the statistics must agree exactly
+(valid counts) or up to summation order (sums).
 """
 import os
 
@@ -23,8 +18,7 @@ import posediffusion_b200 as pdb
 from posediffusion_b200 import _native
 from posediffusion_b200 import synthetic as syn
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PDB_TEST_EXPERIMENTAL") != "1", reason="experimental layout: set PDB_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 FLAGS = ((1, 1, 1), (0, 0, 1), (1, 0, 0), (0, 1, 0))
 
 
@@ -40,11 +34,12 @@ def ctx(dev):
 
 
 def pack(ctx, m, layout):
+    before = ctx.ggs_layout
     ctx.set_ggs_layout(layout)
     try:
         return ctx.pack_matches(m)
     finally:
-        ctx.set_ggs_layout("plain")  # the context is shared with every other test module
+        ctx.set_ggs_layout(before)  # the context is shared with every other test module
 
 
 def nan_close(actual, desired, atol):

@@ -529,3 +529,34 @@ def test_two_devices_in_one_process():
             first = eps.cpu()
         else:
             assert torch.allclose(first, eps.cpu(), atol=1e-6)
+
+
+def test_fused_loop_rejects_wrong_problem_count_and_frame_count(sampler, dev):
+    """B > 1 with a single matches_dict, or a dict whose img_shape[0] differs from the pose's frame count, must
+    raise instead of indexing past the problem array / striding the pose with the wrong frame count."""
+    ctx = sampler.model.native_context()
+    frames = 6
+    m, _, _ = syn.scene_matches(frames, 16, seed=3)
+    cfg = syn.default_ggs_cfg()
+    cfg.update(iter_num=1, verbose=False)
+    cond = partial(pdb.geometry_guided_sampling, matches_dict=m, GGS_cfg=cfg)
+    z2 = syn.random_features(2, frames, 1).to(dev)
+    with pytest.raises(ValueError, match="match sets for a batch"):
+        sampler.p_sample_loop([2, frames, 9], z2, cond, 10)
+    z7 = syn.random_features(1, frames + 1, 1).to(dev)
+    with pytest.raises(ValueError, match="img_shape"):
+        sampler.p_sample_loop([1, frames + 1, 9], z7, cond, 10)
+    # the library itself refuses too (a caller that binds the C ABI directly)
+    import ctypes as C
+    pm = ctx.pack_matches(m)
+    draws = syn.predraw_noise(2, frames, seed=1).to(dev)
+    pose = torch.empty(2, frames, 9, device=dev)
+    conf = _native.ggs_config_struct(cfg)
+    arr = ctx._problem_array([pm])
+    rc = ctx.lib.pdb_sample_loop(ctx.handle, z2.data_ptr(), draws.data_ptr(), 2, frames, arr, 1, C.byref(conf), 10, pose.data_ptr(),
+                                 None, None, None)
+    assert rc == _native.PDB_ERR_INVALID and b"match sets" in ctx.lib.pdb_last_error(ctx.handle)
+    draws7 = syn.predraw_noise(1, frames + 1, seed=1).to(dev)
+    rc = ctx.lib.pdb_sample_loop(ctx.handle, z7.data_ptr(), draws7.data_ptr(), 1, frames + 1, arr, 1, C.byref(conf), 10,
+                                 pose.data_ptr(), None, None, None)
+    assert rc == _native.PDB_ERR_INVALID and b"frames" in ctx.lib.pdb_last_error(ctx.handle)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     lib = _native.load_library()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pdb_abi_version() == 1
+    assert lib.pdb_abi_version() == _native.PDB_ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
@@ -202,3 +202,55 @@ def test_colmap_remap_mirror_matches_reference_function():
     np.testing.assert_allclose(kp1, g["kp1"], rtol=0, atol=1e-4)
     np.testing.assert_allclose(kp2, g["kp2"], rtol=0, atol=1e-4)
     assert colmap_keypoint_to_pytorch3d({(1, 2): None}, keypoints, image_info) == (None, None, None)
+
+
+def test_problem_count_and_frame_checks():
+    """One match set per sequence, each packed for the pose's frame count (the fused loop used to index past the
+    array / stride the pose with the set's frame count)."""
+    class FakeSet:
+        def __init__(self, frames):
+            self.frames = frames
+
+    _native.Context._check_problems([FakeSet(5), FakeSet(5)], 2, 5)
+    with pytest.raises(ValueError, match="1 match sets for a batch of 2"):
+        _native.Context._check_problems([FakeSet(5)], 2, 5)
+    with pytest.raises(ValueError, match="img_shape"):
+        _native.Context._check_problems([FakeSet(5), FakeSet(6)], 2, 5)
+
+
+def test_match_cache_is_keyed_on_content_not_only_identity():
+    import importlib
+
+    ggs_mod = importlib.import_module("posediffusion_b200.geometry_guided_sampling")  # the package attribute is the function
+
+    class FakeCtx:
+        ggs_layout = "plain"
+        device = type("D", (), {"index": 0})()
+
+        def __init__(self):
+            self.packs = 0
+
+        def pack_matches(self, d):
+            self.packs += 1
+            return ("packed", self.packs)
+
+    ctx = FakeCtx()
+    ggs_mod.invalidate_matches()
+    d = {"kp1": np.zeros((10, 2)), "kp2": np.ones((10, 2)), "i12": np.zeros((10, 2), np.int64), "img_shape": (3, 3, 224, 224)}
+    a = ggs_mod.packed_matches(ctx, d)
+    assert ggs_mod.packed_matches(ctx, d) == a and ctx.packs == 1          # cached
+    d["kp1"][0, 0] = 7.0                                                   # in-place edit of a sampled element
+    assert ggs_mod.packed_matches(ctx, d) != a and ctx.packs == 2
+    d["kp2"] = d["kp2"].copy()                                             # a new array object
+    ggs_mod.packed_matches(ctx, d)
+    assert ctx.packs == 3
+    ggs_mod.invalidate_matches(d)                                          # explicit invalidation
+    ggs_mod.packed_matches(ctx, d)
+    assert ctx.packs == 4
+    ctx.ggs_layout = "paired"                                              # a set packed in another stream layout is not reused
+    ggs_mod.packed_matches(ctx, d)
+    assert ctx.packs == 5
+    for i in range(20):                                                    # bounded: at most _KEEP_MAX sets stay pinned
+        ggs_mod.packed_matches(ctx, dict(d, kp1=np.full((10, 2), float(i))))
+    assert len(ggs_mod._KEEP) <= ggs_mod._KEEP_MAX
+    ggs_mod.invalidate_matches()
