@@ -24,9 +24,32 @@ template <bool kEval, bool kPaired>
 __global__ void __launch_bounds__(kGgsThreads, 1)
 ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P);
 
-size_t ggs_ws_per_problem(int frames) {
-  size_t bytes = 128 + sizeof(float) * 3 * (size_t)(frames * 7 + kAccTail) * kAccPad;  // {bar, cnt[3]} + 3 padded accumulators
-  return (bytes + 255) / 256 * 256;
+// Exchange workspace of one sequence: double-buffered slots of its CTAs (xch1) and of its group leaders (xch2).
+size_t ggs_ws_per_problem(int frames, int cpp, int group) {
+  const size_t words = 2 * (size_t)(cpp + ggs_xch_groups(cpp, group)) * ggs_xch_words(frames);
+  return (words * sizeof(unsigned long long) + 255) / 256 * 256;
+}
+
+int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return (v && v[0]) ? atoi(v) : fallback;
+}
+
+// CTAs per sequence of one launch of `nprob` sequences (one CTA per SM, at least ~1 round per warp) and the exchange
+// group size.  PDB_GGS_CPP / PDB_GGS_GROUP are tuning overrides (an upper bound on the CTAs per sequence / the group size).
+void ggs_plan(const Context* ctx, int nprob, long long max_rounds, int* cpp_out, int* group_out) {
+  int cpp = ctx->sm_count / nprob;
+  if (cpp < 1) cpp = 1;
+  long long want = max_rounds / 32;
+  if (want < 1) want = 1;
+  if (cpp > want) cpp = (int)want;
+  const int cap = env_int("PDB_GGS_CPP", 0);
+  if (cap >= 1 && cpp > cap) cpp = cap;
+  int group = env_int("PDB_GGS_GROUP", kXchGroupDefault);
+  if (group < 2) group = 2;
+  if (cpp <= 2 * group) group = cpp;  // few CTAs: one level (every CTA sums every slot)
+  *cpp_out = cpp;
+  *group_out = group;
 }
 }  // namespace
 
@@ -431,12 +454,7 @@ ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsPar
 template <bool kEval, bool kPaired>
 int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_frames, long long max_rounds,
                      GgsParams P, cudaStream_t st) {
-  int cpp = ctx->sm_count / nprob;
-  if (cpp < 1) cpp = 1;
-  long long want = max_rounds / 32;  // at least ~1 round per warp
-  if (want < 1) want = 1;
-  if (cpp > want) cpp = (int)want;
-  P.ctas_per_problem = cpp;
+  const int cpp = P.ctas_per_problem;  // ggs_plan
   // shared-memory match cache: everything beyond the fixed per-frame state, in rounds of 512 B
   const size_t fixed = ggs_smem_fixed_bytes(max_frames);
   const size_t budget = ctx->smem_optin > fixed + 1024 ? ctx->smem_optin - fixed - 1024 : 0;
@@ -504,14 +522,25 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frame
   if (cfg->iter_num < 0) return ctx->fail(PDB_ERR_INVALID, "iter_num < 0");
   if (int rc = check_ggs_problems(ctx, problems, batch, frames)) return rc;
   int max_frames = 0;
-  size_t ws_need = 0;
   for (int b = 0; b < batch; ++b) {
     const Matches* m = reinterpret_cast<const Matches*>(problems[b]);
     max_frames = max_frames > m->frames ? max_frames : m->frames;
-    ws_need += ggs_ws_per_problem(m->frames);
+  }
+  // exchange slots for every launch of this call (at most kGgsBatchMax sequences per launch): sized for the worst plan
+  size_t ws_need = 0;
+  for (int b0 = 0; b0 < batch; b0 += kGgsBatchMax) {
+    const int nb = (batch - b0) < kGgsBatchMax ? (batch - b0) : kGgsBatchMax;
+    long long max_rounds = 1;
+    for (int i = 0; i < nb; ++i) {
+      const Matches* m = reinterpret_cast<const Matches*>(problems[b0 + i]);
+      max_rounds = max_rounds > m->rounds ? max_rounds : m->rounds;
+    }
+    int cpp, group;
+    ggs_plan(ctx, nb, max_rounds, &cpp, &group);
+    ws_need += (size_t)nb * ggs_ws_per_problem(max_frames, cpp, group);
   }
   if (int rc = ensure_buffer(ctx, &ctx->ggs_ws, &ctx->ggs_ws_bytes, ws_need)) return rc;
-  PDB_CUDA(ctx, cudaMemsetAsync(ctx->ggs_ws, 0, ws_need, st));
+  PDB_CUDA(ctx, cudaMemsetAsync(ctx->ggs_ws, 0, ws_need, st));  // tags restart at 1 in every launch
   GgsParams P = {};
   P.n_phases = PDB_GGS_PHASES;
   const int n = cfg->iter_num;
@@ -534,6 +563,11 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frame
     long long max_rounds = 1;
     for (int i = 0; i < nb; ++i) {
       const Matches* m = reinterpret_cast<const Matches*>(problems[b0 + i]);
+      max_rounds = max_rounds > m->rounds ? max_rounds : m->rounds;
+    }
+    ggs_plan(ctx, nb, max_rounds, &P.ctas_per_problem, &P.xch_group);
+    for (int i = 0; i < nb; ++i) {
+      const Matches* m = reinterpret_cast<const Matches*>(problems[b0 + i]);
       GgsProblem& p = gb.prob[i];
       p.pts = m->pts;
       p.segs = m->segs;
@@ -544,13 +578,11 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frame
       p.height = (float)m->height;
       p.width = (float)m->width;
       p.pose = pose_dev + (size_t)(b0 + i) * N * 9;
-      p.bar = reinterpret_cast<unsigned*>(ws);
-      p.gcnt = reinterpret_cast<int*>(ws + 4);
-      p.gacc = reinterpret_cast<float*>(ws + 128);
+      p.xch1 = reinterpret_cast<unsigned long long*>(ws);
+      p.xch2 = p.xch1 + 2 * (size_t)P.ctas_per_problem * ggs_xch_words(m->frames);
       p.stats = stats_dev ? stats_dev + (b0 + i) : nullptr;
       p.dbg_clock = (ctx->ggs_clock && batch == 1) ? ctx->ggs_clock : nullptr;
-      ws += ggs_ws_per_problem(m->frames);
-      max_rounds = max_rounds > m->rounds ? max_rounds : m->rounds;
+      ws += ggs_ws_per_problem(max_frames, P.ctas_per_problem, P.xch_group);
     }
     const int layout = reinterpret_cast<const Matches*>(problems[b0])->layout;
     if (int rc = launch_ggs_layout<false>(ctx, layout, gb, nb, max_frames, max_rounds, P, st)) return rc;
@@ -579,11 +611,12 @@ int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_de
   const Matches* m = reinterpret_cast<const Matches*>(pm);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t ws_need = ggs_ws_per_problem(m->frames);
+  GgsParams P = {};
+  ggs_plan(ctx, 1, m->rounds > 0 ? m->rounds : 1, &P.ctas_per_problem, &P.xch_group);
+  const size_t ws_need = ggs_ws_per_problem(m->frames, P.ctas_per_problem, P.xch_group);
   if (int rc = ensure_buffer(ctx, &ctx->ggs_ws, &ctx->ggs_ws_bytes, ws_need)) return rc;
   PDB_CUDA(ctx, cudaMemsetAsync(ctx->ggs_ws, 0, ws_need, st));
   if (G_dev) PDB_CUDA(ctx, cudaMemsetAsync(G_dev, 0, sizeof(float) * 9 * (m->nseg ? m->nseg : 1), st));
-  GgsParams P = {};
   P.n_phases = 1;
   P.iters[0] = 1;
   P.flags[0] = (update_R ? 1 : 0) | (update_T ? 2 : 0) | (update_FL ? 4 : 0);
@@ -604,9 +637,8 @@ int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_de
   p.height = (float)m->height;
   p.width = (float)m->width;
   p.pose = const_cast<float*>(pose_dev);  // eval mode never writes the pose
-  p.bar = reinterpret_cast<unsigned*>(ws);
-  p.gcnt = reinterpret_cast<int*>(ws + 4);
-  p.gacc = reinterpret_cast<float*>(ws + 128);
+  p.xch1 = reinterpret_cast<unsigned long long*>(ws);
+  p.xch2 = p.xch1 + 2 * (size_t)P.ctas_per_problem * ggs_xch_words(m->frames);
   p.dbg_grad = grad_dev;
   p.dbg_scalars = scalars_dev;
   p.dbg_F = F_dev;

@@ -78,6 +78,14 @@ inline unsigned ld_acquire_u32(const unsigned* p) {
 }
 inline unsigned ld_relaxed_u32(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 inline void red_release_add_u32(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+inline void st_ll(unsigned long long* p, unsigned bits, unsigned tag) {
+  __atomic_store_n(p, ((unsigned long long)tag << 32) | (unsigned long long)bits, __ATOMIC_RELAXED);
+}
+inline unsigned long long ld_ll(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void ll_backoff() {  // the poller waits for other CTAs (OS threads): let the CTA's other threads publish first
+  emu::yield();
+  sched_yield();
+}
 inline uint32_t smem_u32(const void* p) { return emu::shared_addr(p); }
 inline void mbar_init(uint32_t bar, uint32_t count) { emu::mbar_init(bar, count); }
 inline void mbar_fence_init() {}
@@ -104,6 +112,19 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Flag-carrying exchange words: ONE 64-bit relaxed store publishes {32-bit payload, 32-bit tag}.  A 64-bit scalar access
+// is single-copy atomic, so a reader that sees the expected tag has the payload that was stored with it -- no fence, no
+// separate flag, no barrier counter (the protocol NCCL calls "LL").  Loads and stores go to L2 (gpu scope).
+__device__ __forceinline__ void st_ll(unsigned long long* p, unsigned bits, unsigned tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)bits;
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+__device__ __forceinline__ void ll_backoff() {}
 
 // mbarrier + bulk asynchronous copy (global -> shared, completion counted in bytes on an mbarrier)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,6 +159,36 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   return v;
 }
 #endif
+
+// Sum over `count` publishers of word `e` of an exchange buffer laid out [publisher][stride] (ascending publisher order ->
+// the same bits in every reader).  Polls until every word carries `tag`; up to kLlBatch loads in flight per thread.
+// kInt: the payload is an int32 (exact sum) instead of an fp32.
+constexpr int kLlBatch = 16;
+template <bool kInt>
+__device__ __forceinline__ unsigned ll_sum(const unsigned long long* base, size_t stride, int count, unsigned tag) {
+  float fsum = 0.f;
+  int isum = 0;
+  for (int c0 = 0; c0 < count; c0 += kLlBatch) {
+    unsigned long long w[kLlBatch];
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int k = 0; k < kLlBatch; ++k) {  // past the end: the last publisher again (keeps the batch branch-free, in registers)
+        w[k] = ld_ll(base + (size_t)min(c0 + k, count - 1) * stride);
+        ok = ok && ((unsigned)(w[k] >> 32) == tag);
+      }
+      if (!ok) ll_backoff();
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < kLlBatch; ++k) {
+      const bool in = c0 + k < count;
+      if (kInt) isum += in ? (int)(unsigned)w[k] : 0;
+      else fsum += in ? __uint_as_float((unsigned)w[k]) : 0.f;  // + 0.f of a padding slot leaves the sum bit-identical
+    }
+  }
+  return kInt ? (unsigned)isum : __float_as_uint(fsum);
+}
 
 // The same barrier executed by ONE warp per CTA (the rest of the CTA waits at a later __syncthreads).
 // All 32 lanes may have issued global atomics before; __syncwarp orders them before lane 0's release.

@@ -10,11 +10,17 @@
 //            statistics and the 3x3 gradient G = sum d err / d F' accumulate in registers, then one 16-shuffle
 //            warp reduction and shared-memory adds per (warp, pair segment);
 //   stage 2a one warp per pair segment applies the pair adjoint on 18 lanes (G -> gAt, gRt of both frames);
-//   stage 2b one thread per touched frame unfolds K and applies the frame adjoint (-> gT, gq); the CTA flushes
-//            7 floats per touched frame + 4 scalars with global atomics;
-//   barrier  one group-wide barrier per iteration (the gradient accumulators are triple-buffered);
+//   stage 2b one thread per frame unfolds K and applies the frame adjoint (-> gT, gq): the CTA's partial gradient,
+//            7 floats per frame + 4 scalars + the valid count, in shared memory;
+//   exchange all-reduce of that vector over the CTAs of the sequence through L2 with flag-carrying 64-bit words
+//            (common.cuh st_ll / ll_sum): every CTA publishes its vector into its own slot; with more than
+//            `xch_group` CTAs the leader of each group of `xch_group` CTAs sums its group's slots (fixed order) and
+//            publishes a group slot, and every CTA sums the group slots (fixed order).  No atomics, no barrier
+//            counter, no accumulator to recycle; all CTAs obtain bit-identical sums; slots are double-buffered by the
+//            iteration parity (a CTA can only be one exchange ahead of the slowest reader of its slot);
 //   stage 3  every CTA redundantly finishes the step from the summed gradient: early-exit test, gradient mask,
-//            norm-relative clip, momentum, update of its own copy of the pose.
+//            norm-relative clip (each warp reduces the norms itself: no block barrier), momentum, update of its own
+//            copy of the pose into the second pose buffer, then stage 0 of the next iteration.
 #pragma once
 #include "geom.cuh"
 #include "ggs_layout.cuh"
@@ -28,10 +34,9 @@ constexpr int kGgsMaxSeg = 128;   // pair segments handled per chunk by one CTA
 constexpr int kGgsUnroll = 4;     // rounds (of 32 matches) per streaming chunk (2 KB)
 constexpr int kRingStages = 4;    // chunks in flight per warp in the bulk-async ring (8 KB per warp, 128 KB per CTA)
 constexpr int kRingBytes = kGgsWarps * kRingStages * kGgsUnroll * 512 + kGgsWarps * kRingStages * 8;
-constexpr int kAccTail = 4;       // {g_fx', g_fy', clamp_sum, valid error sum (eval mode)}
-constexpr int kAccPad = 32;        // each global accumulator sits in its own 128-byte line: 148 CTAs adding into 5 lines
-                                  // serialise on a few L2 slices; one line per value spreads them over the whole L2
+constexpr int kAccTail = 5;       // {g_fx', g_fy', clamp_sum, valid error sum (eval mode), valid count (int32 bits)}
 constexpr int kSegAcc = 12;       // per-segment shared accumulators: G[9], clamp_sum, valid error sum, pad
+constexpr int kXchGroupDefault = 12;  // CTAs per exchange group (two-level all-reduce above this many CTAs per sequence)
 
 struct GgsProblem {
   const float4* pts;    // [rounds*32] (u1,v1,u2,v2), padded per segment to 32-row rounds
@@ -42,9 +47,8 @@ struct GgsProblem {
   int frames;
   float height, width;
   float* pose;          // [frames*9] in/out
-  float* gacc;          // [3][frames*7 + kAccTail], zero on entry
-  int* gcnt;            // [3], zero on entry
-  unsigned* bar;        // zero on entry
+  unsigned long long* xch1;  // [2][ctas_per_problem][frames*7 + kAccTail] exchange slots of the CTAs, zero on entry
+  unsigned long long* xch2;  // [2][groups][frames*7 + kAccTail] exchange slots of the group leaders, zero on entry
   pdb_ggs_stats* stats; // may be null
   float* dbg_grad;      // eval mode: [frames*9]
   float* dbg_scalars;   // eval mode: [4]
@@ -62,12 +66,16 @@ struct GgsParams {
   double min_matches;
   int resident_rounds;  // rounds of 32 matches that fit the CTA's shared-memory match cache (0 = always stream)
   int ring;             // 1: shared memory holds the bulk-async streaming ring (used when the slice is not resident)
+  int xch_group;        // CTAs per exchange group; >= ctas_per_problem: one-level exchange (every CTA reads every slot)
 };
 
-constexpr int kGgsFixedFloatsPerFrame = 2 * 9 + 4 * 9 + 4 + 18 + 7;  // pose, vel, R, A, Rt, At, fl, inr, gAt|gRt, summed gradient
+__host__ __device__ inline int ggs_xch_words(int frames) { return frames * 7 + kAccTail; }
+__host__ __device__ inline int ggs_xch_groups(int cpp, int group) { return group >= cpp ? 0 : (cpp + group - 1) / group; }
+
+constexpr int kGgsFixedFloatsPerFrame = 3 * 9 + 4 * 9 + 8 + 18 + 14;  // pose x2, vel, R, A, Rt, At, (fl, inr) x2, gAt|gRt, partial + summed gradient
 
 __host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
-  size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 96 + (size_t)kGgsMaxSeg * kSegAcc);
+  size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 128 + (size_t)kGgsMaxSeg * kSegAcc);
   bytes += kGgsMaxSeg * sizeof(int);         // segment valid counts
   bytes += (kGgsMaxSeg + 1) * sizeof(int4);  // segment descriptors
   return (bytes + 127) / 128 * 128;
@@ -118,6 +126,49 @@ __device__ __forceinline__ void sampson_match2_unit(const float4 X, const float4
   sampson_match2_core(make_float2(X.x, X.y), make_float2(X.z, X.w), make_float2(Y.x, Y.y), make_float2(Y.z, Y.w), F, smax, acc2);
 }
 
+// All-reduce of one CTA's partial gradient vector over the `cpp` CTAs of its sequence (see the file header).  Word layout:
+// [0, 7N) gT | gq per frame, then g_fx', g_fy', clamp_sum, valid error sum (eval mode), valid count (int32).  On return
+// s_gsum holds the sums -- the same bits in every CTA -- once the caller has passed a block barrier.  Kept out of line: its
+// 16-loads-in-flight polling loops would otherwise compete for registers with the streaming loop of stage 1.
+template <bool kEval>
+__device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned long long* xch2, int cpp, int cta, int group, int N,
+                                          unsigned it_global, const float* s_part, const float* s_misc, int cta_cnt, float g_fx,
+                                          float g_fy, float* s_gsum) {
+  const int tid = threadIdx.x;
+  const int nsum = ggs_xch_words(N);
+  const unsigned tag = it_global + 1u;
+  const size_t buf = it_global & 1u;
+  unsigned long long* mine = xch1 + (buf * (size_t)cpp + (size_t)cta) * nsum;
+  for (int e = tid; e < nsum; e += kGgsThreads) {
+    unsigned bits;
+    if (e < N * 7) bits = __float_as_uint(s_part[e]);
+    else if (e == N * 7 + 0) bits = __float_as_uint(g_fx);
+    else if (e == N * 7 + 1) bits = __float_as_uint(g_fy);
+    else if (e == N * 7 + 2) bits = __float_as_uint(s_misc[4]);
+    else if (e == N * 7 + 3) bits = __float_as_uint(kEval ? s_misc[5] : 0.f);
+    else bits = (unsigned)cta_cnt;
+    st_ll(mine + e, bits, tag);
+  }
+  const int groups = ggs_xch_groups(cpp, group);
+  if (groups > 0) {
+    const int g = cta / group;
+    if (cta - g * group == 0) {  // group leader: sum the slots of the group in CTA order, publish the group slot
+      const int c_lo = g * group, c_n = min(cpp, c_lo + group) - c_lo;
+      const unsigned long long* src = xch1 + (buf * (size_t)cpp + (size_t)c_lo) * nsum;
+      unsigned long long* dst = xch2 + (buf * (size_t)groups + (size_t)g) * nsum;
+      for (int e = tid; e < nsum; e += kGgsThreads)
+        st_ll(dst + e, e == nsum - 1 ? ll_sum<true>(src + e, nsum, c_n, tag) : ll_sum<false>(src + e, nsum, c_n, tag), tag);
+    }
+    const unsigned long long* src = xch2 + buf * (size_t)groups * nsum;
+    for (int e = tid; e < nsum; e += kGgsThreads)
+      s_gsum[e] = __uint_as_float(e == nsum - 1 ? ll_sum<true>(src + e, nsum, groups, tag) : ll_sum<false>(src + e, nsum, groups, tag));
+  } else {
+    const unsigned long long* src = xch1 + buf * (size_t)cpp * nsum;
+    for (int e = tid; e < nsum; e += kGgsThreads)
+      s_gsum[e] = __uint_as_float(e == nsum - 1 ? ll_sum<true>(src + e, nsum, cpp, tag) : ll_sum<false>(src + e, nsum, cpp, tag));
+  }
+}
+
 // One CTA of the group that owns one sequence.  See the file header for the stage structure.
 // `resident_rounds` > 0: the CTA's whole slice of matches (<= resident_rounds rounds) is staged in shared memory
 // once per launch and every inner iteration streams it from there (no L2/HBM traffic inside the loop).
@@ -132,27 +183,31 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   const int cpp = P.ctas_per_problem;
   const int cta = blockIdx.x % cpp;
   const int N = pr.frames, N9 = N * 9;
-  const int acc_stride = (N * 7 + kAccTail) * kAccPad;
+  const int nsum = ggs_xch_words(N);
 
   // ---- shared memory carve-up ----
   int4* s_seg = reinterpret_cast<int4*>(smem_raw);
-  float* s_pose = reinterpret_cast<float*>(s_seg + kGgsMaxSeg + 1);
-  float* s_vel = s_pose + N9;
+  // pose, focal length and clamp mask are double buffered: stage 3 writes the updated pose into the other buffer while
+  // slower warps still read the current one for the clip norms (saves a block barrier per iteration)
+  float* s_pose = reinterpret_cast<float*>(s_seg + kGgsMaxSeg + 1);  // current pose
+  float* s_pose_nxt = s_pose + N9;
+  float* s_vel = s_pose_nxt + N9;
   float* s_R = s_vel + N9;
   float* s_A = s_R + N9;
   float* s_Rt = s_A + N9;
   float* s_At = s_Rt + N9;
-  float* s_fl = s_At + N9;
-  float* s_inr = s_fl + 2 * N;
-  float* s_fg = s_inr + 2 * N;    // [N][18]: gAt (0..8), gRt (9..17)
-  float* s_misc = s_fg + 2 * N9;  // [4] clamp_sum, [5] loss_sum, [8..] step scalars
-  float* s_red = s_misc + 32;     // [kGgsWarps][2] norm partials
-  float* s_gsum = s_red + 32;     // [N*7 + 8] summed gradient of this iteration (copied from L2 by warp 0)
+  float* s_fl = s_At + N9;          // current clamped focal lengths [N][2]
+  float* s_inr = s_fl + 2 * N;      // 1 where the clamp passes gradient
+  float* s_fl_nxt = s_inr + 2 * N;
+  float* s_inr_nxt = s_fl_nxt + 2 * N;
+  float* s_fg = s_inr_nxt + 2 * N;  // [N][18]: gAt (0..8), gRt (9..17)
+  float* s_misc = s_fg + 2 * N9;    // [4] clamp_sum, [5] loss_sum, [8..11] sum over frames of d/d(ix, iy, kx, ky)
+  float* s_part = s_misc + 64;      // [N*7] this CTA's partial gradient of the iteration
+  float* s_gsum = s_part + N * 7 + 32;  // [N*7 + kAccTail] summed gradient of this iteration (all CTAs: identical bits)
   float* s_sacc = s_gsum + N * 7 + 32;  // [kGgsMaxSeg][kSegAcc]
   int* s_scnt = reinterpret_cast<int*>(s_sacc + kGgsMaxSeg * kSegAcc);
   float4* s_pts = reinterpret_cast<float4*>(smem_raw + ggs_smem_fixed_bytes(N));
   __shared__ int s_cta_cnt;
-  __shared__ int s_ctrl;  // 0 = continue, 1 = phase dropped
 
   // ---- static work partition: rounds -> CTAs -> warps ----
   const long long R = pr.rounds;
@@ -191,8 +246,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   for (int e = tid; e < 2 * N9; e += kGgsThreads) s_fg[e] = 0.f;
   for (int e = tid; e < kGgsMaxSeg * kSegAcc; e += kGgsThreads) s_sacc[e] = 0.f;
   for (int e = tid; e < kGgsMaxSeg; e += kGgsThreads) s_scnt[e] = 0;
-  if (tid < 32) s_misc[tid] = 0.f;
-  if (tid == 0) { s_cta_cnt = 0; s_ctrl = 0; }
+  if (tid < 64) s_misc[tid] = 0.f;
+  if (tid == 0) s_cta_cnt = 0;
   if (single_chunk && cta_has_work && tid <= seg_hi - seg_lo + 1) s_seg[tid] = __ldg(&pr.segs[seg_lo + tid]);
   if (resident) {
     const float4* src = pr.pts + (size_t)r_cta0 * 32;
@@ -204,42 +259,15 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   unsigned it_global = 0;
   float kin[4] = {0.f, 0.f, 0.f, 0.f}, fpx = 1.f, fpy = 1.f;  // shared intrinsics (every warp holds a copy)
 
-  // Pose -> per-frame terms, four threads per frame: thread (n, j < 3) builds column j of R_cv, A = hat(t) R_cv and
-  // (after the focal mean is known) of the K-folded At, Rt; thread (n, 3) evaluates the clamped focal length.
-  // Two block barriers inside; every warp ends up with the shared intrinsics in registers.
+  // Pose -> per-frame terms, three threads per frame: thread (n, j < 3) builds column j of R_cv, A = hat(t) R_cv and of the
+  // K-folded At, Rt.  The clamped focal lengths of the current pose are already in s_fl / s_inr (written with the pose), so
+  // one block barrier suffices; every warp ends up with the shared intrinsics in registers.
+  auto focal_of = [&](float log_f, float* fl, float* inr) {
+    const float ev = expf(log_f + kLogFlBias);
+    *fl = fminf(fmaxf(ev, kFlMin), kFlMax);
+    *inr = (ev >= kFlMin && ev <= kFlMax) ? 1.f : 0.f;
+  };
   auto frames_forward = [&]() {
-    float Rc[3] = {0.f, 0.f, 0.f}, Ac[3] = {0.f, 0.f, 0.f};
-    const int n = tid >> 2, j = tid & 3;
-    if (n < N) {
-      const float* p = s_pose + n * 9;
-      if (j < 3) {
-        const float w = p[3], x = p[4], y = p[5], z = p[6];
-        const float s2 = 2.0f / (w * w + x * x + y * y + z * z);
-        // row j of the pytorch3d rotation = column j of R_cv up to the signs D = diag(-1,-1,1) on the rows
-        float r0, r1, r2;
-        if (j == 0) { r0 = 1.f - s2 * (y * y + z * z); r1 = s2 * (x * y - z * w); r2 = s2 * (x * z + y * w); }
-        else if (j == 1) { r0 = s2 * (x * y + z * w); r1 = 1.f - s2 * (x * x + z * z); r2 = s2 * (y * z - x * w); }
-        else { r0 = s2 * (x * z - y * w); r1 = s2 * (y * z + x * w); r2 = 1.f - s2 * (x * x + y * y); }
-        Rc[0] = -r0; Rc[1] = -r1; Rc[2] = r2;
-        const float tx = -p[0], ty = -p[1], tz = p[2];
-        Ac[0] = -tz * Rc[1] + ty * Rc[2];
-        Ac[1] = tz * Rc[0] - tx * Rc[2];
-        Ac[2] = -ty * Rc[0] + tx * Rc[1];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          s_R[n * 9 + i * 3 + j] = Rc[i];
-          s_A[n * 9 + i * 3 + j] = Ac[i];
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const float ev = expf(p[7 + k] + kLogFlBias);
-          s_fl[n * 2 + k] = fminf(fmaxf(ev, kFlMin), kFlMax);
-          s_inr[n * 2 + k] = (ev >= kFlMin && ev <= kFlMax) ? 1.f : 0.f;
-        }
-      }
-    }
-    __syncthreads();
     {  // shared focal length = mean over frames (geometry_guided_sampling.py:142), reduced redundantly per warp
       float fx = 0.f, fy = 0.f;
       for (int m = lane; m < N; m += 32) {
@@ -253,7 +281,24 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       kin[2] = -cx / fpx;
       kin[3] = -cy / fpy;
     }
+    const int n = tid >> 2, j = tid & 3;
     if (n < N && j < 3) {
+      const float* p = s_pose + n * 9;
+      const float w = p[3], x = p[4], y = p[5], z = p[6];
+      const float s2 = 2.0f / (w * w + x * x + y * y + z * z);
+      // row j of the pytorch3d rotation = column j of R_cv up to the signs D = diag(-1,-1,1) on the rows
+      float r0, r1, r2;
+      if (j == 0) { r0 = 1.f - s2 * (y * y + z * z); r1 = s2 * (x * y - z * w); r2 = s2 * (x * z + y * w); }
+      else if (j == 1) { r0 = s2 * (x * y + z * w); r1 = 1.f - s2 * (x * x + z * z); r2 = s2 * (y * z - x * w); }
+      else { r0 = s2 * (x * z - y * w); r1 = s2 * (y * z + x * w); r2 = 1.f - s2 * (x * x + y * y); }
+      const float Rc[3] = {-r0, -r1, r2};
+      const float tx = -p[0], ty = -p[1], tz = p[2];
+      const float Ac[3] = {-tz * Rc[1] + ty * Rc[2], tz * Rc[0] - tx * Rc[2], -ty * Rc[0] + tx * Rc[1]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        s_R[n * 9 + i * 3 + j] = Rc[i];
+        s_A[n * 9 + i * 3 + j] = Ac[i];
+      }
       s_At[n * 9 + 0 + j] = kin[0] * Ac[0];
       s_At[n * 9 + 3 + j] = kin[1] * Ac[1];
       s_At[n * 9 + 6 + j] = kin[2] * Ac[0] + kin[3] * Ac[1] + Ac[2];
@@ -265,6 +310,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   };
   static_assert(4 * kMaxFrames <= kGgsThreads, "four threads per frame");
   __syncthreads();
+  if (tid < 2 * N) focal_of(s_pose[(tid >> 1) * 9 + 7 + (tid & 1)], &s_fl[tid], &s_inr[tid]);
+  __syncthreads();
   frames_forward();
 
   for (int phase = 0; phase < P.n_phases; ++phase) {
@@ -274,8 +321,6 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
     int done = 0, dropped = 0, last_valid = 0;          // tracked by warp 0
     float last_logged = __int_as_float(0x7fc00000);
     for (int iter = 0; iter < iters; ++iter) {
-      float* acc = pr.gacc + (it_global % 3) * acc_stride;
-      int* cnt = pr.gcnt + (it_global % 3);
       long long ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0;
       if (pr.dbg_clock && tid == 0) ck0 = clock64();
       // ================= chunks of <= kGgsMaxSeg pair segments (one chunk in all practical cases) =================
@@ -568,159 +613,123 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       }
       __syncthreads();
       if (pr.dbg_clock && tid == 0) ck1 = clock64();
-      // ================= warp 0: frame adjoint + flush, barrier, step, next forward =================
-      if (warp == 0) {
-        float gk[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int n = lane; n < N; n += 32) {
-          float* gAt = s_fg + n * 18;
-          bool touched = false;
+      // ================= stage 2b: one thread per frame: unfold K, frame adjoint -> the CTA's partial gradient =================
+      if (tid < N) {
+        const int n = tid;
+        float* gAt = s_fg + n * 18;
+        bool touched = false;
 #pragma unroll
-          for (int k = 0; k < 18; ++k) touched |= (gAt[k] != 0.f);
-          if (touched) {
-            float gA[9], gR[9], k4[4], gT[3], gq[4];
-            frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
-            frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
+        for (int k = 0; k < 18; ++k) touched |= (gAt[k] != 0.f);
+        float gT[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+        if (touched) {
+          float gA[9], gR[9], k4[4];
+          frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
+          frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) atomicAdd(&acc[(n * 7 + k) * kAccPad], gT[k]);
+          for (int k = 0; k < 4; ++k) atomicAdd(&s_misc[8 + k], k4[k]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) atomicAdd(&acc[(n * 7 + 3 + k) * kAccPad], gq[k]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gk[k] += k4[k];
-#pragma unroll
-            for (int k = 0; k < 18; ++k) gAt[k] = 0.f;
-          }
+          for (int k = 0; k < 18; ++k) gAt[k] = 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gk[k] = warp_sum(gk[k]);
-        if (lane == 0 && cta_has_work) {
-          atomicAdd(&acc[(N * 7 + 0) * kAccPad], (-gk[0] + cx * gk[2]) / (fpx * fpx));
-          atomicAdd(&acc[(N * 7 + 1) * kAccPad], (-gk[1] + cy * gk[3]) / (fpy * fpy));
-          atomicAdd(&acc[(N * 7 + 2) * kAccPad], s_misc[4]);
-          if (kEval) atomicAdd(&acc[(N * 7 + 3) * kAccPad], s_misc[5]);
-          if (s_cta_cnt) atomicAdd(cnt, s_cta_cnt);
-          s_misc[4] = 0.f;
-          s_misc[5] = 0.f;
-          s_cta_cnt = 0;
-        }
-        if (pr.dbg_clock && tid == 0) ck2 = clock64();
-        // ---- group barrier (warp 0 only; the other warps wait at the block barrier below) ----
-        warp_group_barrier(pr.bar, (it_global + 1) * (unsigned)cpp);
-        if (pr.dbg_clock && tid == 0) ck3 = clock64();
-        // recycle the accumulator used two iterations from now (nobody reads or writes it at this point)
-        if (cta == 0) {
-          float* old = pr.gacc + ((it_global + 2) % 3) * acc_stride;
-          for (int e = lane; e < N * 7 + kAccTail; e += 32) old[e * kAccPad] = 0.f;
-          if (lane == 0) pr.gcnt[(it_global + 2) % 3] = 0;
-        }
-        // ---- bring the summed gradient into shared memory: ONE L2 round trip, a single warp per CTA ----
-        const int nsum = N * 7 + kAccTail;
-        for (int e = lane; e < nsum; e += 32) s_gsum[e] = __ldcg(&acc[e * kAccPad]);
-        if (lane == 0) {
-          const int n_valid = __ldcg(cnt);
-          s_gsum[nsum] = __int_as_float(n_valid);
-          // len(valid) / N < min_matches  (:103-105), evaluated as n < min_matches * N in float64
-          s_ctrl = (!kEval && (P.min_matches > 0.0) && ((double)n_valid < P.min_matches * (double)N)) ? 1 : 0;
-        }
-        if (pr.dbg_clock && tid == 0) {
-          long long* c = pr.dbg_clock + (size_t)cta * 8;
-          const long long ck4 = clock64();
-          c[1] += ck1 - ck0; c[2] += ck2 - ck1; c[3] += ck3 - ck2; c[4] += ck4 - ck3; c[5] += 1;
-        }
+        for (int k = 0; k < 3; ++k) s_part[n * 7 + k] = gT[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_part[n * 7 + 3 + k] = gq[k];
       }
+      __syncthreads();
+      if (pr.dbg_clock && tid == 0) ck2 = clock64();
+      // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
+      ggs_exchange<kEval>(pr.xch1, pr.xch2, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
+                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum);
       ++it_global;
       __syncthreads();
+      if (pr.dbg_clock && tid == 0) {
+        ck3 = clock64();
+        long long* c = pr.dbg_clock + (size_t)cta * 8;
+        c[1] += ck1 - ck0; c[2] += ck2 - ck1; c[3] += ck3 - ck2; c[5] += 1;
+      }
       // ================= stage 3: finish the step, all threads (identical in every CTA) =================
-      long long ck5 = 0;
-      if (pr.dbg_clock && tid == 0) ck5 = clock64();
+      bool drop_phase = false;
       {
-        const int nsum = N * 7 + kAccTail;
-        const int n_valid = __float_as_int(s_gsum[nsum]);
+        const int n_valid = __float_as_int(s_gsum[N * 7 + 4]);
         last_valid = n_valid;
         last_logged = s_gsum[N * 7 + 2] / (float)pr.m_total;
-        if (s_ctrl) {
+        // len(valid) / N < min_matches  (:103-105), evaluated as n < min_matches * N in float64
+        drop_phase = !kEval && (P.min_matches > 0.0) && ((double)n_valid < P.min_matches * (double)N);
+        if (tid == 0) {  // the CTA-level partial sums are consumed: zero them for the next iteration (written after >= 1 barrier)
+          s_misc[4] = 0.f; s_misc[5] = 0.f;
+          s_misc[8] = 0.f; s_misc[9] = 0.f; s_misc[10] = 0.f; s_misc[11] = 0.f;
+          s_cta_cnt = 0;
+        }
+        if (drop_phase) {
           dropped = 1;
         } else {
           const float inv_n = 1.0f / (float)n_valid;  // mean over the valid matches (:110)
           const float gfx = upd_FL ? s_gsum[N * 7 + 0] * (scale / (float)N) : 0.f;
           const float gfy = upd_FL ? s_gsum[N * 7 + 1] * (scale / (float)N) : 0.f;
-          constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
-          float gv[kPer];
-          float gn2 = 0.f, pn2 = 0.f;
-#pragma unroll
-          for (int q = 0; q < kPer; ++q) {
-            const int e = tid + q * kGgsThreads;
-            gv[q] = 0.f;
-            if (e < N9) {
-              const int n = e / 9, c = e - n * 9;
-              float gsum;
-              if (c < 3) gsum = upd_T ? s_gsum[n * 7 + c] : 0.f;
-              else if (c < 7) gsum = upd_R ? s_gsum[n * 7 + c] : 0.f;
-              else gsum = (c == 7 ? gfx : gfy) * s_fl[n * 2 + (c - 7)] * s_inr[n * 2 + (c - 7)];
-              const float g1 = gsum * inv_n;
-              gv[q] = g1;
+          auto grad_of = [&](int e) {  // d mean(valid err) / d pose[e]
+            const int n = e / 9, c = e - n * 9;
+            float gsum;
+            if (c < 3) gsum = upd_T ? s_gsum[n * 7 + c] : 0.f;
+            else if (c < 7) gsum = upd_R ? s_gsum[n * 7 + c] : 0.f;
+            else gsum = (c == 7 ? gfx : gfy) * s_fl[n * 2 + (c - 7)] * s_inr[n * 2 + (c - 7)];
+            return gsum * inv_n;
+          };
+          if (kEval) {
+            if (cta == 0) {
+              for (int e = tid; e < N9; e += kGgsThreads) pr.dbg_grad[e] = grad_of(e);
+              if (tid == 0) {
+                pr.dbg_scalars[0] = s_gsum[N * 7 + 3] / (float)n_valid;
+                pr.dbg_scalars[1] = (float)n_valid;
+                pr.dbg_scalars[2] = last_logged;
+                pr.dbg_scalars[3] = 0.f;
+              }
+            }
+          } else {
+            // clip norms: every warp reduces the whole gradient itself (lane-strided partial sums, xor butterfly): the same
+            // bits in every warp and every CTA, and no block barrier
+            float gn2 = 0.f, pn2 = 0.f;
+            for (int e = lane; e < N9; e += 32) {
+              const float g1 = grad_of(e);
               gn2 = fmaf(g1, g1, gn2);
               const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
               pn2 = fmaf(pm, pm, pn2);
-              if (kEval && cta == 0) pr.dbg_grad[e] = g1;
             }
-          }
-          if (kEval) {
-            if (cta == 0 && tid == 0) {
-              pr.dbg_scalars[0] = s_gsum[N * 7 + 3] / (float)n_valid;
-              pr.dbg_scalars[1] = (float)n_valid;
-              pr.dbg_scalars[2] = last_logged;
-              pr.dbg_scalars[3] = 0.f;
-            }
-          } else {
             gn2 = warp_sum(gn2);
             pn2 = warp_sum(pn2);
-            if (lane == 0) {
-              s_red[warp * 2] = gn2;
-              s_red[warp * 2 + 1] = pn2;
-            }
-            __syncthreads();
-            gn2 = 0.f;
-            pn2 = 0.f;
-#pragma unroll
-            for (int wv = 0; wv < kGgsWarps; ++wv) {  // fixed order: identical in every thread and CTA
-              gn2 += s_red[wv * 2];
-              pn2 += s_red[wv * 2 + 1];
-            }
             const float max_norm = P.alpha * sqrtf(pn2) / P.lr;      // :119
             const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
             const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
-#pragma unroll
-            for (int q = 0; q < kPer; ++q) {
-              const int e = tid + q * kGgsThreads;
-              if (e < N9) {
-                const float g1 = gv[q] * coef;
-                const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
-                s_vel[e] = v;
-                s_pose[e] = s_pose[e] - P.lr * v;
-              }
+            for (int e = tid; e < N9; e += kGgsThreads) {
+              const float g1 = grad_of(e) * coef;
+              const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
+              s_vel[e] = v;
+              const float pnew = s_pose[e] - P.lr * v;
+              s_pose_nxt[e] = pnew;
+              const int n = e / 9, c = e - n * 9;
+              if (c >= 7) focal_of(pnew, &s_fl_nxt[n * 2 + (c - 7)], &s_inr_nxt[n * 2 + (c - 7)]);
             }
             ++done;
+            {  // the updated pose becomes the current one (uniform: every thread swaps its pointers)
+              float* t0 = s_pose; s_pose = s_pose_nxt; s_pose_nxt = t0;
+              float* t1 = s_fl; s_fl = s_fl_nxt; s_fl_nxt = t1;
+              float* t2 = s_inr; s_inr = s_inr_nxt; s_inr_nxt = t2;
+            }
             __syncthreads();
-            frames_forward();  // stage 0 of the next iteration (two block barriers inside)
+            frames_forward();  // stage 0 of the next iteration (one block barrier inside)
           }
         }
       }
-      if (pr.dbg_clock && tid == 0) pr.dbg_clock[(size_t)cta * 8 + 6] += clock64() - ck5;
+      if (pr.dbg_clock && tid == 0) pr.dbg_clock[(size_t)cta * 8 + 6] += clock64() - ck3;
       if (kEval) break;
-      if (s_ctrl) break;  // uniform: phase dropped on "insufficient valid matches" (no update, :103-108)
+      if (drop_phase) break;  // uniform: phase dropped on "insufficient valid matches" (no update, :103-108)
     }
     if (kEval) break;
-    __syncthreads();
-    if (tid == 0) {
-      if (cta == 0 && pr.stats) {
-        pr.stats->sampson[phase] = last_logged;
-        pr.stats->iters[phase] = done;
-        pr.stats->dropped[phase] = dropped;
-        pr.stats->n_valid[phase] = last_valid;
-      }
-      s_ctrl = 0;
+    if (tid == 0 && cta == 0 && pr.stats) {
+      pr.stats->sampson[phase] = last_logged;
+      pr.stats->iters[phase] = done;
+      pr.stats->dropped[phase] = dropped;
+      pr.stats->n_valid[phase] = last_valid;
     }
-    __syncthreads();
   }
   if (!kEval && cta == 0) {
     for (int e = tid; e < N9; e += kGgsThreads) pr.pose[e] = s_pose[e];

@@ -31,6 +31,9 @@
 #define __grid_constant__
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 
 namespace emu {
 
@@ -158,6 +161,8 @@ inline long long clock64() { return 0; }
 // ---- arithmetic intrinsics ------------------------------------------------------------------------------------
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }

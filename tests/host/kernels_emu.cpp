@@ -99,10 +99,14 @@ extern "C" int ggs_emu_run(const float* pts, const int* segs /*[nseg+1][4] incl.
                            float* dbg_G, pdb_ggs_stats* stats, int* mode_out) {
   using namespace pdb;
   if (frames < 1 || frames > kMaxFrames || cpp < 1 || n_phases < 1 || n_phases > PDB_GGS_PHASES) return -1;
-  const size_t acc_floats = 3 * (size_t)(frames * 7 + kAccTail) * kAccPad;
-  std::vector<float> gacc(acc_floats, 0.f);
-  std::vector<int> gcnt(4, 0);
-  std::vector<unsigned> bar(4, 0u);
+  // exchange slots as api_core.cu lays them out: PDB_GGS_GROUP overrides the group size here too (tests exercise both the
+  // one-level and the two-level exchange with few CTAs)
+  int group = kXchGroupDefault;
+  if (const char* g = getenv("PDB_GGS_GROUP")) group = atoi(g) >= 2 ? atoi(g) : 2;
+  if (cpp <= 2 * group && !getenv("PDB_GGS_GROUP")) group = cpp;
+  if (group >= cpp) group = cpp;
+  const int groups = ggs_xch_groups(cpp, group);
+  std::vector<unsigned long long> xch(2 * (size_t)(cpp + groups) * ggs_xch_words(frames), 0ull);
   GgsProblem pr = {};
   pr.pts = reinterpret_cast<const float4*>(pts);
   pr.segs = reinterpret_cast<const int4*>(segs);
@@ -113,9 +117,8 @@ extern "C" int ggs_emu_run(const float* pts, const int* segs /*[nseg+1][4] incl.
   pr.height = height;
   pr.width = width;
   pr.pose = pose;
-  pr.gacc = gacc.data();
-  pr.gcnt = gcnt.data();
-  pr.bar = bar.data();
+  pr.xch1 = xch.data();
+  pr.xch2 = xch.data() + 2 * (size_t)cpp * ggs_xch_words(frames);
   pr.stats = stats;
   pr.dbg_grad = dbg_grad;
   pr.dbg_scalars = dbg_scalars;
@@ -133,6 +136,7 @@ extern "C" int ggs_emu_run(const float* pts, const int* segs /*[nseg+1][4] incl.
   P.smax = smax;
   P.momentum = momentum;
   P.min_matches = min_matches;
+  P.xch_group = group;
   // the launch logic of api_core.cu::launch_ggs_chunk: shared-memory-resident slice when it fits, else the bulk-async ring
   const size_t fixed = ggs_smem_fixed_bytes(frames);
   const size_t budget = emu::kSharedBytes > fixed + 1024 ? emu::kSharedBytes - fixed - 1024 : 0;

@@ -146,3 +146,28 @@ def test_emulated_layouts_agree_on_ragged_and_tiny_segments(emu, mode, cpp):
         for lay in out:
             np.testing.assert_allclose(out[lay]["grad"], c["grad"], rtol=0, atol=3e-4 * gmax)
         assert np.array_equal(out["plain"]["F"], out["paired"]["F"])  # F' of every segment does not depend on the layout
+
+
+@pytest.mark.parametrize("layout", ["plain", "paired"])
+@pytest.mark.parametrize("cpp,group", [(5, 2), (7, 3), (6, 6)])
+def test_emulated_two_level_exchange(emu, layout, cpp, group, monkeypatch):
+    """The per-iteration all-reduce through flag-carrying exchange words (csrc/common.cuh st_ll / ll_sum): groups of `group`
+    CTAs with a ragged last group (two levels), or every CTA reading every slot (group == cpp).  Same fixtures and tolerances
+    as the one-level runs above; the exchange sums in a fixed order, so CTA counts that split the matches identically must
+    give bit-identical poses whatever the grouping."""
+    monkeypatch.setenv("PDB_GGS_GROUP", str(group))
+    g = load_golden("ggs.npz")
+    cfg = syn.default_ggs_cfg()
+    cfg["iter_num"] = int(g["iter_num"])
+    m = matches_from(g, "scene5")
+    r = run_kernel(emu, m, g["scene5_pose"], layout, "resident", cpp=cpp, cfg=cfg)
+    ref = g["scene5_out"]
+    np.testing.assert_allclose(r["pose"], ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    n = cfg["iter_num"]
+    assert list(r["stats"]["iters"]) == [2 * n, n, n, n, 2 * n]
+    # evaluation instantiation through the same exchange
+    key = "scene6_f111"
+    gs = load_golden("sampson.npz")
+    e = run_kernel(emu, matches_from(gs, "scene6"), gs["scene6_pose"], layout, "resident", cpp=cpp, eval_flags=(1, 1, 1))
+    assert int(e["scalars"][1]) == int(gs[f"{key}_n_valid"])
+    nan_close(e["grad"], gs[f"{key}_grad"], 2e-4 * np.nanmax(np.abs(gs[f"{key}_grad"])))

@@ -6,7 +6,9 @@ Scenes are geometry-consistent (`syn.scene_matches`), so that about half of the 
 gradient.  Both match-stream layouts run.
 
 Tolerances, stated once:
-  * gradient: 3e-4 * max|grad| against the float64 closed form (`oracle.sampson_f64.sampson_closed_form_f64_large`);
+  * gradient: 1e-3 * max|grad| against the float64 closed form (`oracle.sampson_f64.sampson_closed_form_f64_large`).  fp32 is
+    the limit at this size: the reference's own operator sequence in fp32 (`po.sampson_terms` + autograd) is 3.3e-4 * max|grad|
+    away from the float64 result on the config-3 scene, the CUDA path 3.3e-4 as well (measured, round 2);
   * valid count: validity is an fp32 comparison `err < sampson_max` on an error computed with a different (fused) operation
     order than the reference's, so a match whose float64 error lies within 1e-5 (relative) of the threshold may flip.  The
     oracle counts those matches (`band`); the device count must lie within max(2, band) of the oracle's;
@@ -64,7 +66,7 @@ def check_eval(ctx, dev, m, start, ref, layout, flags=(True, True, True)):
     n_valid = int(round(sc[1].item()))
     assert abs(n_valid - ref["n_valid"]) <= max(2, ref["band"]), (n_valid, ref["n_valid"], ref["band"])
     gmax = np.abs(ref["grad"]).max()
-    np.testing.assert_allclose(grad.cpu().numpy(), ref["grad"], rtol=0, atol=3e-4 * gmax)
+    np.testing.assert_allclose(grad.cpu().numpy(), ref["grad"], rtol=0, atol=1e-3 * gmax)
     np.testing.assert_allclose(sc[2].item(), ref["logged"], rtol=1e-4)
     np.testing.assert_allclose(sc[0].item(), ref["loss"], rtol=1e-4)
 
@@ -129,8 +131,6 @@ def test_full_loop_ggs_on_teacher_forced_on_oracle_trajectory(dev):
     cfg.update(min_matches=0, verbose=False)
     z = syn.random_features(1, frames, 31)
     draws = syn.predraw_noise(1, frames, seed=31)
-    # the random-weight trajectory is unrelated to the scene: scale the initial state down so that poses stay in a regime
-    # where matches are valid and the guided steps do real work
     cond_o = partial(po.geometry_guided_sampling, matches_dict=m, GGS_cfg=cfg)
     _, ref = po.p_sample_loop(net, sched, z, draws, cond_o, 10)
     assert torch.isfinite(ref).all()
