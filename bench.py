@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- diffusion steps/sec of the PoseDiffusion sampling hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg1|cfg2|cfg4|cfg5]
     (N > 1: launched by torchrun, one rank per GPU over NCCL)
 
 A bench "step" is one full p_sample_loop of the workload: T = 100 diffusion steps of one 20-frame sequence per GPU,
@@ -33,6 +33,7 @@ import torch
 T_STEPS = 100
 WORKLOADS = {
     # name: (frames, matches per ordered pair or 0 for GGS off, description)
+    "cfg1": (5, 0, "BASELINE configs[0]: 1 sequence x 5 frames (the samples/apple demo shape), T=100, GGS off (the reference's CPU-runnable case)"),
     "cfg3": (20, 2048, "BASELINE configs[2]: 1 sequence x 20 frames per GPU, T=100, GGS on (start_step 10, 700 inner iters/step), "
                       "M=2048 uniform-random matches for each of the 380 ordered pairs (778240 matches)"),
     "cfg2": (20, 0, "BASELINE configs[1]: 1 sequence x 20 frames per GPU, T=100, GGS off (denoiser-only path)"),
@@ -96,45 +97,97 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (the reference is Python and does not exist on the GPU box; oracle/pose_oracle.py
-# restates it operator for operator in PyTorch-CPU, see its header).  Bounded sample, extrapolated.
+# CPU arm.  The reference is Python: its unmodified `models` / `util` packages are imported from /root/reference (build
+# container) or from baseline/_ref (installed by oracle/install_reference.py; what the GPU box has) behind the pytorch3d /
+# hydra shim of oracle/shims -> kind "reference".  If neither exists the oracle port (oracle/pose_oracle.py, the same operator
+# sequence restated) is timed instead -> kind "port".  Bounded sample, extrapolated to the full loop.
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(frames: int, per_pair: int, seed: int, threads: int, budget_s: float):
-    from functools import partial
+def host_thread_candidates():
+    """BASELINE.md section 3 asks for os.cpu_count() threads; PyTorch-CPU is often faster with fewer on these ~1e6-element ops,
+    so the arm times a short probe with each candidate and keeps the faster (both are reported)."""
+    n = os.cpu_count() or 1
+    forced = os.environ.get("PDB_REF_THREADS")
+    if forced:
+        return [max(1, min(n, int(forced)))]
+    return sorted({n, min(n, 32)}, reverse=True)
+
+
+def cpu_reference_run(frames: int, per_pair: int, seed: int, budget_s: float):
+    import contextlib
+    import io
 
     from oracle import pose_oracle as po
+    from oracle import ref_loader
     from posediffusion_b200 import synthetic as syn
 
-    torch.set_num_threads(threads)
     state = syn.random_denoiser_state(seed)
-    net = po.build_denoiser(state)
-    sched = po.diffusion_schedule()
     z = syn.random_features(1, frames, seed)
     draws = syn.predraw_noise(1, frames, seed=seed)
-    with torch.no_grad():
-        po.p_sample(net, sched, draws[0], 99, z, draws[1])  # warm-up
+    cfg = syn.default_ggs_cfg()
+    kind = "reference" if ref_loader.reference_available() else "port"
+    if kind == "reference":
+        ref = ref_loader.load_reference()
+        sampler = ref_loader.build_reference_sampler(ref, state)
+
+        def denoise_loop():  # GaussianDiffusion.sample without guidance: 100 x (Denoiser.forward + DDPM update)
+            with torch.no_grad():
+                return sampler.sample(shape=[1, frames, 9], z=z)[0]
+
+        def ggs_call(mean, matches, k=1):  # one geometry_guided_sampling call with iter_num = k: 2k+k+k+k+2k = 7k inner iterations
+            with contextlib.redirect_stdout(io.StringIO()):  # the reference prints one line per phase
+                return ref.geometry_guided_sampling(mean, 5, matches, dict(cfg, iter_num=k, min_matches=0)), 7 * k
+    else:
+        net = po.build_denoiser(state)
+        sched = po.diffusion_schedule()
+
+        def denoise_loop():
+            return po.p_sample_loop(net, sched, z, draws, None, 0)[0]
+
+        def ggs_call(mean, matches, k=1):
+            return po.geometry_guided_sampling(mean, 5, matches, dict(cfg, iter_num=k, min_matches=0)), 7 * k
+
+    m = syn.uniform_matches(frames, per_pair, seed=seed) if per_pair else None
+    probe = {}
+    for threads in host_thread_candidates():  # short probe per candidate thread count
+        torch.set_num_threads(threads)
+        t0 = time.perf_counter()
+        if m is not None:
+            ggs_call(draws[0].clone(), m)
+        else:
+            with torch.no_grad():
+                denoise_loop()
+        probe[threads] = time.perf_counter() - t0
+    threads = min(probe, key=probe.get)
+    torch.set_num_threads(threads)
+    denoise_loop() if m is None else None  # warm-up of the path not probed above is the probe itself
     t0 = time.perf_counter()
-    pose, _ = po.p_sample_loop(net, sched, z, draws, None, 0)  # 100 denoiser + DDPM steps
+    pose = denoise_loop()
     t_denoise = time.perf_counter() - t0
     sample = f"100 denoiser steps ({t_denoise:.2f} s)"
-    inner_total, t_inner, n_inner = 0, 0.0, 0
-    if per_pair > 0:
-        m = syn.uniform_matches(frames, per_pair, seed=seed)
-        prep = po.prepare_matches(m)
-        cfg = syn.default_ggs_cfg()
-        inner_total = cfg["start_step"] * 7 * cfg["iter_num"]  # 10 guided steps x (2+1+1+1+2) x 100
-        # time all-parameter GGS iterations (every phase costs the same forward + backward) until the budget is spent
-        mean = pose.clone()
-        po.ggs_phase(mean, prep, iter_num=1, min_matches=0)  # warm-up (2 iterations)
+    t_ggs_full = 0.0
+    if m is not None:
+        # one guided step = one geometry_guided_sampling call = match upload / preprocessing U + 700 inner iterations.  Calls with
+        # iter_num = 1 and 3 (7 and 21 inner iterations) alternate until the budget is spent; the least-squares line
+        # T(call) = U + n_inner * t_iter separates the per-call cost from the per-iteration cost, and the full loop is
+        # start_step x (U + 700 t_iter).
+        inner_per_step = 7 * cfg["iter_num"]
+        mean = pose.detach().clone()
+        xs, ys = [], []
         t_start = time.perf_counter()
-        while time.perf_counter() - t_start < budget_s:
+        while time.perf_counter() - t_start < budget_s or len(xs) < 2:
+            k = 1 if len(xs) % 2 == 0 else 3
             t1 = time.perf_counter()
-            mean = po.ggs_phase(mean, prep, iter_num=1, min_matches=0)  # all flags on -> iter_num doubles: 2 iterations
-            t_inner += time.perf_counter() - t1
-            n_inner += 2
-        sample += f" + {n_inner} of {inner_total} inner GGS iterations ({t_inner:.2f} s), extrapolated"
-    wall = t_denoise + (inner_total * t_inner / n_inner if n_inner else 0.0)
-    return {"steps_per_s": T_STEPS / wall, "wall_s_full": wall, "sample": sample, "threads": threads}
+            mean, did = ggs_call(mean, m, k)
+            ys.append(time.perf_counter() - t1)
+            xs.append(did)
+        t_iter, per_call = np.polyfit(np.asarray(xs, float), np.asarray(ys, float), 1)
+        per_call = max(0.0, float(per_call))
+        t_ggs_full = cfg["start_step"] * (per_call + inner_per_step * float(t_iter))
+        sample += (f" + {int(sum(xs))} of {cfg['start_step'] * inner_per_step} inner GGS iterations in {len(xs)} calls ({sum(ys):.2f} s): "
+                   f"{1e3 * t_iter:.1f} ms per inner iteration, {1e3 * per_call:.0f} ms per call (match upload), extrapolated")
+    sample += "; probe s per thread count: " + ", ".join(f"{k} threads {v:.2f}" for k, v in sorted(probe.items()))
+    wall = t_denoise + t_ggs_full
+    return {"steps_per_s": T_STEPS / wall, "wall_s_full": wall, "sample": sample, "threads": threads, "kind": kind}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -290,17 +343,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # PyTorch-CPU scales poorly past ~32 threads on these ~1e6-element ops (128-thread runs are slower): use the
-        # host threads it can use, capped at 32, and say so in `cores`
-        threads = min(os.cpu_count() or 1, int(os.environ.get("PDB_REF_THREADS", "32")))
-        res = cpu_reference_run(frames, per_pair, args.seed, threads, args.cpu_budget * max(1, args.steps))
+        res = cpu_reference_run(frames, per_pair, args.seed, args.cpu_budget * max(1, args.steps))
         line = {
             "impl": "reference", "metric": "diffusion steps/sec (20-frame seq, GGS on)", "value": res["steps_per_s"],
             "unit": "diffusion steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * res["wall_s_full"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "timesteps": T_STEPS},
-            "cpu_baseline": {"value": res["steps_per_s"], "unit": "diffusion steps/s", "cores": res["threads"], "kind": "port",
+            "cpu_baseline": {"value": res["steps_per_s"], "unit": "diffusion steps/s", "cores": res["threads"], "kind": res["kind"],
                              "sample": res["sample"]},
             "e2e": {"value": res["steps_per_s"], "unit": "diffusion steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -466,9 +516,8 @@ def main():
                     "ring (from HBM at config 5: 414 MB per iteration; largely from L2 when the sequences' match sets fit its 126 MB)",
         }
     if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only
-        threads = min(os.cpu_count() or 1, 32)
-        res = cpu_reference_run(frames, per_pair, args.seed, threads, args.cpu_budget)
-        line["cpu_baseline"] = {"value": res["steps_per_s"], "unit": "diffusion steps/s", "cores": res["threads"], "kind": "port",
+        res = cpu_reference_run(frames, per_pair, args.seed, args.cpu_budget)
+        line["cpu_baseline"] = {"value": res["steps_per_s"], "unit": "diffusion steps/s", "cores": res["threads"], "kind": res["kind"],
                                 "sample": res["sample"], "wall_s_full_extrapolated": res["wall_s_full"]}
     print(json.dumps(line))
     if world > 1:

@@ -1,7 +1,8 @@
 """Import the reference's OWN hot-path modules from /root/reference (build container only).
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so this is used by
-`oracle/make_golden.py` (fixture generation) and by CPU tests that skip when it is absent.
+TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box; there the same unmodified modules are imported from
+baseline/_ref (installed by oracle/install_reference.py).  Used by `oracle/make_golden.py` (fixture generation), by CPU tests
+that skip when neither is present, and by `bench.py --impl reference` / the `cpu_baseline` leg.
 pytorch3d and hydra are not installed here; `oracle/shims/` restates the handful of symbols
 the reference imports.  Nothing is copied: the modules are imported in place.
 """
@@ -13,6 +14,9 @@ from types import SimpleNamespace
 
 REFERENCE_ROOT = os.environ.get("POSEDIFF_REFERENCE_ROOT", "/root/reference")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+# the unmodified `models` / `util` packages installed by oracle/install_reference.py (git-ignored; present on the GPU box)
+INSTALLED_ROOT = os.environ.get("POSEDIFF_INSTALLED_REFERENCE",
+                                os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref"))
 
 TRANSFORMER_CFG = dict(
     _target_="models.TransformerEncoderWrapper",
@@ -26,16 +30,28 @@ TRANSFORMER_CFG = dict(
 )  # cfgs/default.yaml:27-35
 
 
+def reference_path() -> str | None:
+    """Directory that holds the reference's `models` and `util` packages: the source tree in the build container, else the
+    copy installed into baseline/_ref (what the GPU box has), else None."""
+    src = os.path.join(REFERENCE_ROOT, "pose_diffusion")
+    if os.path.isdir(os.path.join(src, "models")):
+        return src
+    if os.path.isdir(os.path.join(INSTALLED_ROOT, "models")) and os.path.isdir(os.path.join(INSTALLED_ROOT, "util")):
+        return INSTALLED_ROOT
+    return None
+
+
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pose_diffusion", "models"))
+    return reference_path() is not None
 
 
 def load_reference() -> SimpleNamespace:
     """Returns namespace(Denoiser, GaussianDiffusion, geometry_guided_sampling, GGS_optimize,
     compute_sampson_distance, pose_encoding_to_camera, get_fundamental_matrices, to_attr)."""
-    if not reference_available():
-        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
-    for path in (os.path.join(REFERENCE_ROOT, "pose_diffusion"), _SHIMS):
+    where = reference_path()
+    if where is None:
+        raise FileNotFoundError(f"reference modules not found under {REFERENCE_ROOT} or {INSTALLED_ROOT}")
+    for path in (where, _SHIMS):
         if path not in sys.path:
             sys.path.insert(0, path)
     import hydra.utils as hydra_utils  # the shim

@@ -3,6 +3,10 @@
 //
 //   mode 0  round-1 scheme: red.global.add into one 128-byte line per value, release/acquire counter barrier, read-back
 //   mode 1  flag-carrying words ("LL": one 64-bit store = {fp32 value, iteration tag}), ONE level: every CTA reads all slots
+//   mode 3  two levels with plain data + one release flag per slot (flag-first polling)
+//   mode 4  hop calibration (two CTAs bounce one word)
+//   mode 6  two levels with 16-byte {3 values, tag} words (counts torn words)
+//   mode 7  mode 2 with 16 loads in flight per thread (the kernel's setting)
 //   mode 2  LL, TWO levels: groups of S CTAs, the group leader sums its group's slots and publishes a group slot,
 //           every CTA then reads the G group slots
 //
@@ -41,12 +45,50 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// sum of word e over `count` publishers [publisher][words], polling for `tag`; B loads in flight
+template <int B>
+__device__ __forceinline__ float ll_sum_f(const unsigned long long* base, size_t stride, int count, unsigned tag) {
+  float sum = 0.f;
+  for (int c0 = 0; c0 < count; c0 += B) {
+    unsigned long long w[B];
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        w[k] = ld_ll(base + (size_t)min(c0 + k, count - 1) * stride);
+        ok = ok && ((unsigned)(w[k] >> 32) == tag);
+      }
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < B; ++k) sum += (c0 + k < count) ? __uint_as_float((unsigned)w[k]) : 0.f;
+  }
+  return sum;
+}
+__device__ __forceinline__ void st_v4(float4* p, float4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 struct Params {
   int mode, words, iters, S, G, replicas;
   float* acc;                 // mode 0: [3][words*32]
   unsigned* bar;              // mode 0
   unsigned long long* slot1;  // [2][ctas][words]
   unsigned long long* slot2;  // [2][replicas][G][words]
+  unsigned* flags;            // modes 3: [2][ctas + G] flag words, one 128-byte line each
+  float* plain1;              // mode 3: [2][ctas][words]
+  float* plain2;              // mode 3: [2][G][words]
+  float4* vec1;               // mode 6: [2][ctas][words/3+1]
+  float4* vec2;               // mode 6: [2][G][words/3+1]
+  unsigned* torn;             // mode 6: count of torn 16-byte words observed
   float* out;                 // [ctas] checksum
   long long* cycles;          // [ctas]
 };
@@ -103,6 +145,114 @@ __global__ void __launch_bounds__(512, 1) xchg_kernel(const Params P) {
         }
         s_sum[e] = sum;
       }
+      __syncthreads();
+    } else if (P.mode == 3) {
+      // flag-first: plain data stores, __syncthreads, ONE release store of a per-slot flag; readers poll the flags with one
+      // lane per slot, then read the data with plain (L2) loads
+      const int S = P.S, G = P.G;
+      float* mys = P.plain1 + ((size_t)(it & 1) * C + cta) * P.words;
+      for (int e = tid; e < P.words; e += blockDim.x) __stcg(mys + e, contrib);
+      __syncthreads();
+      unsigned* fl = P.flags + (size_t)(it & 1) * (C + G) * 32;
+      if (tid == 0) st_release_u32(fl + cta * 32, tag);
+      const int g = cta / S;
+      if (cta % S == 0) {
+        const int c_lo = g * S, c_hi = min(C, c_lo + S);
+        if (tid < c_hi - c_lo) while (ld_acquire_u32(fl + (c_lo + tid) * 32) != tag) {}
+        __syncthreads();
+        const float* base = P.plain1 + (size_t)(it & 1) * C * P.words;
+        float* dst = P.plain2 + ((size_t)(it & 1) * G + g) * P.words;
+        for (int e = tid; e < P.words; e += blockDim.x) {
+          float sum = 0.f;
+          for (int c = c_lo; c < c_hi; ++c) sum += __ldcg(base + (size_t)c * P.words + e);
+          __stcg(dst + e, sum);
+        }
+        __syncthreads();
+        if (tid == 0) st_release_u32(fl + (C + g) * 32, tag);
+      }
+      if (tid < G) while (ld_acquire_u32(fl + (C + tid) * 32) != tag) {}
+      __syncthreads();
+      const float* base2 = P.plain2 + (size_t)(it & 1) * G * P.words;
+      for (int e = tid; e < P.words; e += blockDim.x) {
+        float sum = 0.f;
+        for (int gg = 0; gg < G; ++gg) sum += __ldcg(base2 + (size_t)gg * P.words + e);
+        s_sum[e] = sum;
+      }
+      __syncthreads();
+    } else if (P.mode == 6) {
+      // 16-byte words {v0, v1, v2, tag}: three values per store; NOT formally single-copy atomic -> torn words are counted
+      const int S = P.S, G = P.G, W4 = (P.words + 2) / 3;
+      float4* mys = P.vec1 + ((size_t)(it & 1) * C + cta) * W4;
+      for (int e = tid; e < W4; e += blockDim.x) st_v4(mys + e, make_float4(contrib, contrib, contrib, __uint_as_float(tag)));
+      const int g = cta / S;
+      auto sum4 = [&](const float4* base, size_t stride, int count) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c0 = 0; c0 < count; c0 += 8) {
+          float4 w[8];
+          bool ok;
+          do {
+            ok = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              w[k] = ld_v4(base + (size_t)min(c0 + k, count - 1) * stride);
+              ok = ok && (__float_as_uint(w[k].w) == tag);
+            }
+          } while (!ok);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (c0 + k < count) {
+              if (w[k].x != w[k].y || w[k].y != w[k].z) atomicAdd(P.torn, 1u);
+              acc.x += w[k].x; acc.y += w[k].y; acc.z += w[k].z;
+            }
+        }
+        return acc;
+      };
+      if (cta % S == 0) {
+        const int c_lo = g * S, c_n = min(C, c_lo + S) - c_lo;
+        const float4* base = P.vec1 + ((size_t)(it & 1) * C + c_lo) * W4;
+        for (int e = tid; e < W4; e += blockDim.x) {
+          float4 a = sum4(base + e, W4, c_n);
+          a.y = a.x; a.z = a.x;  // keep the torn-word check meaningful at level 2
+          a.w = __uint_as_float(tag);
+          st_v4(P.vec2 + ((size_t)(it & 1) * G + g) * W4 + e, a);
+        }
+      }
+      const float4* base2 = P.vec2 + (size_t)(it & 1) * G * W4;
+      for (int e = tid; e < W4; e += blockDim.x) {
+        const float4 a = sum4(base2 + e, W4, G);
+        s_sum[3 * e] = a.x;
+        if (3 * e + 1 < P.words) s_sum[3 * e + 1] = a.y;
+        if (3 * e + 2 < P.words) s_sum[3 * e + 2] = a.z;
+      }
+      __syncthreads();
+    } else if (P.mode == 7) {
+      // mode 2 with 16 loads in flight per thread (what csrc/ggs.cuh does)
+      const int S = P.S, G = P.G;
+      unsigned long long* mys = P.slot1 + ((size_t)(it & 1) * C + cta) * P.words;
+      for (int e = tid; e < P.words; e += blockDim.x) st_ll(mys + e, contrib, tag);
+      const int g = cta / S;
+      if (cta % S == 0) {
+        const int c_lo = g * S, c_n = min(C, c_lo + S) - c_lo;
+        const unsigned long long* base = P.slot1 + ((size_t)(it & 1) * C + c_lo) * P.words;
+        for (int e = tid; e < P.words; e += blockDim.x)
+          st_ll(P.slot2 + ((size_t)(it & 1) * G + g) * P.words + e, ll_sum_f<16>(base + e, P.words, c_n, tag), tag);
+      }
+      const unsigned long long* base2 = P.slot2 + (size_t)(it & 1) * G * P.words;
+      for (int e = tid; e < P.words; e += blockDim.x) s_sum[e] = ll_sum_f<16>(base2 + e, P.words, G, tag);
+      __syncthreads();
+    } else if (P.mode == 4) {
+      // hop calibration: CTA 0 and CTA 1 bounce one word; everybody else idles (two hops per iteration)
+      if (cta < 2 && tid == 0) {
+        unsigned long long* a = P.slot1, *b = P.slot1 + 64;
+        if (cta == 0) {
+          st_ll(a, 1.0f, tag);
+          while ((unsigned)(ld_ll(b) >> 32) != tag) {}
+        } else {
+          while ((unsigned)(ld_ll(a) >> 32) != tag) {}
+          st_ll(b, 1.0f, tag);
+        }
+      }
+      if (tid < P.words + 1) s_sum[tid] = 0.f;
       __syncthreads();
     } else {
       const int S = P.S, G = P.G;
@@ -210,20 +360,31 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&P.bar, 256));
   CK(cudaMalloc(&P.slot1, sizeof(unsigned long long) * 2 * maxC * words));
   CK(cudaMalloc(&P.slot2, sizeof(unsigned long long) * 2 * 8 * 64 * words));
+  CK(cudaMalloc(&P.flags, sizeof(unsigned) * 2 * (maxC + 64) * 32));
+  CK(cudaMalloc(&P.plain1, sizeof(float) * 2 * maxC * words));
+  CK(cudaMalloc(&P.plain2, sizeof(float) * 2 * 64 * words));
+  CK(cudaMalloc(&P.vec1, sizeof(float4) * 2 * maxC * (words / 3 + 1)));
+  CK(cudaMalloc(&P.vec2, sizeof(float4) * 2 * 64 * (words / 3 + 1)));
+  CK(cudaMalloc(&P.torn, 256));
+  CK(cudaMemset(P.torn, 0, 256));
   CK(cudaMalloc(&P.out, sizeof(float) * maxC));
   CK(cudaMalloc(&P.cycles, sizeof(long long) * maxC));
   CK(cudaFuncSetAttribute(xchg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   struct Case { int mode, C, S, rep; };
   std::vector<Case> cases;
-  for (int C : {18, 37, 74, 148}) {
+  cases.push_back({4, 2, 1, 1});
+  cases.push_back({4, 148, 1, 1});
+  for (int C : {18, 74, 148}) {
     cases.push_back({0, C, 0, 1});
-    cases.push_back({1, C, 0, 1});
-    for (int S : {4, 8, 12, 16, 24})
-      if (S < C) cases.push_back({2, C, S, 1});
+    for (int S : {4, 6, 8, 10, 12, 14, 16})
+      if (S < C) {
+        cases.push_back({7, C, S, 1});
+        if (S == 8 || S == 12 || S == 16) {
+          cases.push_back({3, C, S, 1});
+          cases.push_back({6, C, S, 1});
+        }
+      }
   }
-  cases.push_back({2, 148, 12, 2});
-  cases.push_back({2, 148, 12, 4});
-  cases.push_back({2, 148, 8, 4});
   for (const Case& c : cases) {
     P.mode = c.mode;
     P.S = c.S;
@@ -244,6 +405,9 @@ int main(int argc, char** argv) {
       CK(cudaMemset(P.acc, 0, sizeof(float) * 3 * words * 32));
       CK(cudaMemset(P.slot1, 0, sizeof(unsigned long long) * 2 * maxC * words));
       CK(cudaMemset(P.slot2, 0, sizeof(unsigned long long) * 2 * 8 * 64 * words));
+      CK(cudaMemset(P.flags, 0, sizeof(unsigned) * 2 * (maxC + 64) * 32));
+      CK(cudaMemset(P.vec1, 0, sizeof(float4) * 2 * maxC * (words / 3 + 1)));
+      CK(cudaMemset(P.vec2, 0, sizeof(float4) * 2 * 64 * (words / 3 + 1)));
       CK(cudaEventRecord(a));
       CK(cudaLaunchCooperativeKernel((void*)xchg_kernel, dim3(c.C), dim3(512), args, 64 * 1024, 0));
       CK(cudaEventRecord(b));
@@ -253,8 +417,10 @@ int main(int argc, char** argv) {
       if (ms < best) best = ms;
       CK(cudaMemcpy(&chk, P.out, sizeof(float), cudaMemcpyDeviceToHost));
     }
-    printf("mode %d  ctas %3d  S %2d G %2d rep %d : %8.3f us per all-reduce   (check %.3f)\n", c.mode, c.C, c.S, P.G, c.rep,
-           best * 1e3f / iters, chk);
+    unsigned torn = 0;
+    CK(cudaMemcpy(&torn, P.torn, 4, cudaMemcpyDeviceToHost));
+    printf("mode %d  ctas %3d  S %2d G %2d rep %d : %8.3f us per all-reduce   (check %.3f, torn %u)\n", c.mode, c.C, c.S, P.G, c.rep,
+           best * 1e3f / iters, chk, torn);
   }
   return 0;
 }
