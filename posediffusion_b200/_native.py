@@ -258,7 +258,8 @@ class Context:
         self._ok(self.lib.pdb_profile_read(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "pdb_profile_read")
         return a.value, b.value, c.value, d.value
 
-    def ggs_clocks(self, enable: bool = True, read: bool = False):
+    def ggs_clocks(self, enable=True, read: bool = False):
+        """Stage timing probe: enable = True / 1 for the GGS kernel, 2 for the fp32 denoiser kernel (same buffer)."""
         out = np.zeros((256, 8), dtype=np.int64) if read else None
         self._ok(self.lib.pdb_debug_ggs_clocks(self.handle, int(enable), out.ctypes.data if read else None, 256), "pdb_debug_ggs_clocks")
         return out

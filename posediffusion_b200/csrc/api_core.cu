@@ -137,11 +137,13 @@ int pdb_profile_read(pdb_context* c, double* ggs_ms, int64_t* ggs_launches, doub
   return PDB_OK;
 }
 
-// Debug probe: per-CTA cycle sums of the GGS stages {stage0, stage1+2a, stage2b, barrier, stage3, iterations}.
+// Debug probe: per-CTA cycle sums of the GGS stages {-, stage1+2a, stage2b, exchange, -, iterations, stage3+0} (enable = 1) or of
+// the fp32 denoiser kernel {barrier, tile load + LayerNorm, linear item, attention, tail, steps} (enable = 2).
 int pdb_debug_ggs_clocks(pdb_context* c, int32_t enable, int64_t* out, int32_t max_ctas) {
   if (!c) return PDB_ERR_INVALID;
   Context* ctx = reinterpret_cast<Context*>(c);
   PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->den_clock = enable == 2;
   if (enable && !ctx->ggs_clock) {
     ctx->ggs_clock_ctas = ctx->sm_count;
     PDB_CUDA(ctx, cudaMalloc(&ctx->ggs_clock, sizeof(long long) * 8 * ctx->ggs_clock_ctas));
@@ -581,7 +583,7 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frame
       p.xch1 = reinterpret_cast<unsigned long long*>(ws);
       p.xch2 = p.xch1 + 2 * (size_t)P.ctas_per_problem * ggs_xch_words(m->frames);
       p.stats = stats_dev ? stats_dev + (b0 + i) : nullptr;
-      p.dbg_clock = (ctx->ggs_clock && batch == 1) ? ctx->ggs_clock : nullptr;
+      p.dbg_clock = (ctx->ggs_clock && !ctx->den_clock && batch == 1) ? ctx->ggs_clock : nullptr;
       ws += ggs_ws_per_problem(max_frames, P.ctas_per_problem, P.xch_group);
     }
     const int layout = reinterpret_cast<const Matches*>(problems[b0])->layout;

@@ -153,6 +153,7 @@ int enqueue_denoiser(Context* ctx, DenoiserRun run, cudaStream_t st) {
   run.ff = ws;    ws += (size_t)S * kFF;
   run.u = ws;
   PDB_CUDA(ctx, cudaMemsetAsync(run.bar, 0, 256, st));
+  run.dbg_clock = ctx->den_clock ? ctx->ggs_clock : nullptr;  // pdb_debug_ggs_clocks(enable = 2): probe the denoiser instead
   const int TS = pick_token_tile(S);
   const int tiles = (S + TS - 1) / TS;
   int grid = tiles * (3 * kDM / kFPI);  // widest stage (QKV)

@@ -31,6 +31,7 @@ struct Context {
   // stage timing probe of the GGS kernel (debug): [ctas][8] cycle sums
   long long* ggs_clock = nullptr;
   int ggs_clock_ctas = 0;
+  bool den_clock = false;  // the probe buffer is handed to the denoiser kernel instead of the GGS kernel
   // tensor-core engine: one captured CUDA graph of a whole diffusion step, replayed once per step (t lives on the device)
   cudaGraphExec_t tc_graph = nullptr;
   std::vector<size_t> tc_graph_key;

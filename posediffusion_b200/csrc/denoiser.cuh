@@ -77,6 +77,7 @@ struct DenoiserRun {
   // workspace
   float *zproj, *h, *qkv, *att, *ff, *u;
   unsigned* bar;           // zero on entry
+  long long* dbg_clock;    // may be null: [ctas][8] cycle sums {barrier, tile load + LayerNorm, linear item, attention, tail, steps}
 };
 
 inline size_t denoiser_ws_floats(int tokens) {
@@ -401,8 +402,12 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
   const int G = gridDim.x;
   unsigned bar_count = 0;
   // Group barrier: release by one thread after the block barrier (cumulative over the CTA's writes), acquire polls.
+  long long clk[5] = {0, 0, 0, 0, 0};  // stage timing probe (thread 0, only with R.dbg_clock)
+  const bool probe = R.dbg_clock != nullptr && threadIdx.x == 0;
   auto barrier = [&]() {
     ++bar_count;
+    long long c0 = 0;
+    if (probe) c0 = clock64();
     __syncthreads();
     if (threadIdx.x == 0) {
       red_release_add_u32(R.bar, 1u);
@@ -410,6 +415,7 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
       }
     }
     __syncthreads();
+    if (probe) clk[0] += clock64() - c0;
   };
   // One linear stage: Y = epi(X' W^T + ...), work items = (token tile, 32-feature group).  The weights of this CTA's
   // first item are requested BEFORE the barrier that closes the previous stage (`need_barrier`), the activations after.
@@ -428,12 +434,19 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
     for (; item < n_items; item += G) {
       const int tt = item / groups, fg = item - tt * groups;
       if (item != (int)blockIdx.x) linear_prefetch<K>(wreg, Wp, O, fg * kFPI);
+      long long c0 = 0, c1 = 0;
+      if (probe) c0 = clock64();
       if (tt != staged_tile) {
         load_x(tt);
         staged_tile = tt;
       }
       __syncthreads();
+      if (probe) c1 = clock64();
       linear_item<TS, K>(wreg, Xs, red, fg * kFPI, bias, add1, ld1, add2, add_rs, rs, Y, ldy, tt * TS, S, epi);
+      if (probe) {
+        clk[1] += c1 - c0;
+        clk[2] += clock64() - c1;
+      }
     }
   };
   bool pending = false;  // a stage has written global activations that the next stage must wait for
@@ -462,9 +475,12 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
       // attention per (sequence, head)
       barrier();
       {
+        long long c0 = 0;
+        if (probe) c0 = clock64();
         const int chunks = (R.frames + kDenWarps - 1) / kDenWarps;
         for (int item = blockIdx.x; item < R.batch * kHeads * chunks; item += G)
           attention_item(Xs, R.qkv, R.att, item / (kHeads * chunks), (item / chunks) % kHeads, item % chunks, R.frames);
+        if (probe) clk[3] += clock64() - c0;
       }
       // out-proj + residual (in place on h: each element is read and written by the same thread)
       linear_stage(std::integral_constant<int, kDM>{}, L.w_out, kDM,
@@ -486,10 +502,18 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
     // tail: one warp per token
     barrier();
     {
+      long long c0 = 0;
+      if (probe) c0 = clock64();
       const int warp_global = blockIdx.x * kDenWarps + (threadIdx.x >> 5);
       for (int s = warp_global; s < S; s += G * kDenWarps) tail_token(W, R, s, t, t == R.t_lo);
+      if (probe) clk[4] += clock64() - c0;
     }
     pending = true;
+  }
+  if (probe) {
+    long long* c = R.dbg_clock + (size_t)blockIdx.x * 8;
+    for (int k = 0; k < 5; ++k) c[k] += clk[k];
+    c[5] += R.t_hi - R.t_lo + 1;
   }
 }
 

@@ -41,15 +41,34 @@ def init_from_env(backend: str) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+_GATHER_BUFFERS: dict = {}
+
+
 def gather_poses(local: torch.Tensor, total: int) -> torch.Tensor:
-    """All-gather the per-rank [B_local, N, 9] poses into [total, N, 9] in global sequence order."""
+    """All-gather the per-rank [B_local, N, 9] poses into [total, N, 9] in global sequence order.
+
+    One `all_gather_into_tensor` on buffers that are allocated once per (shape, device) and reused: with equal blocks per
+    rank (the benchmark configurations) the collective writes straight into the result and nothing else is launched; ragged
+    blocks are padded to the widest one and compacted by one index_select."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
-    world, rank = dist.get_world_size(), dist.get_rank()
+    world = dist.get_world_size()
     sizes = [shard_range(total, r, world) for r in range(world)]
     widest = max(hi - lo for lo, hi in sizes)
-    padded = local.new_zeros((widest,) + tuple(local.shape[1:]))
-    padded[: local.shape[0]] = local
-    out: List[torch.Tensor] = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(out, padded)
-    return torch.cat([out[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    tail = tuple(local.shape[1:])
+    key = (local.device, local.dtype, widest, world, tail, total)
+    bufs = _GATHER_BUFFERS.get(key)
+    if bufs is None:
+        out = torch.empty((world * widest,) + tail, device=local.device, dtype=local.dtype)
+        pad = None if all(hi - lo == widest for lo, hi in sizes) else torch.zeros((widest,) + tail, device=local.device, dtype=local.dtype)
+        keep = None
+        if pad is not None:
+            keep = torch.tensor([r * widest + i for r, (lo, hi) in enumerate(sizes) for i in range(hi - lo)], device=local.device)
+        bufs = _GATHER_BUFFERS[key] = (out, pad, keep)
+    out, pad, keep = bufs
+    src = local.contiguous()
+    if pad is not None:
+        pad[: local.shape[0]] = local
+        src = pad
+    dist.all_gather_into_tensor(out, src)
+    return out if keep is None else out.index_select(0, keep)
