@@ -25,9 +25,12 @@ __global__ void __launch_bounds__(kGgsThreads, 1)
 ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P);
 
 // Exchange workspace of one sequence: double-buffered slots of its CTAs (xch1) and of its group leaders (xch2).
-size_t ggs_ws_per_problem(int frames, int cpp, int group) {
+size_t ggs_ws_slots_bytes(int frames, int cpp, int group) {
   const size_t words = 2 * (size_t)(cpp + ggs_xch_groups(cpp, group)) * ggs_xch_words(frames);
   return (words * sizeof(unsigned long long) + 255) / 256 * 256;
+}
+size_t ggs_ws_per_problem(int frames, int cpp, int group) {  // slots + the three accumulator buffers of the one-hop exchange
+  return ggs_ws_slots_bytes(frames, cpp, group) + (sizeof(float) * 3 * (size_t)ggs_xch_words(frames) * kAccStride + 255) / 256 * 256;
 }
 
 int env_int(const char* name, int fallback) {
@@ -51,6 +54,7 @@ void ggs_plan(const Context* ctx, int nprob, long long max_rounds, int* cpp_out,
   *cpp_out = cpp;
   *group_out = group;
 }
+int ggs_xch_mode() { return env_int("PDB_GGS_XCH", 1) == 0 ? 0 : 1; }  // PDB_GGS_XCH=0: exchange through flag-carrying slots
 }  // namespace
 
 extern "C" {
@@ -137,7 +141,7 @@ int pdb_profile_read(pdb_context* c, double* ggs_ms, int64_t* ggs_launches, doub
   return PDB_OK;
 }
 
-// Debug probe: per-CTA cycle sums of the GGS stages {-, stage1+2a, stage2b, exchange, -, iterations, stage3+0} (enable = 1) or of
+// Debug probe: per-CTA cycle sums of the GGS stages {-, stage1, stage2b, exchange, stage2a, iterations, stage3+0} (enable = 1) or of
 // the fp32 denoiser kernel {barrier, tile load + LayerNorm, linear item, attention, tail, steps} (enable = 2).
 int pdb_debug_ggs_clocks(pdb_context* c, int32_t enable, int64_t* out, int32_t max_ctas) {
   if (!c) return PDB_ERR_INVALID;
@@ -568,6 +572,7 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frame
       max_rounds = max_rounds > m->rounds ? max_rounds : m->rounds;
     }
     ggs_plan(ctx, nb, max_rounds, &P.ctas_per_problem, &P.xch_group);
+    P.xch_mode = ggs_xch_mode();
     for (int i = 0; i < nb; ++i) {
       const Matches* m = reinterpret_cast<const Matches*>(problems[b0 + i]);
       GgsProblem& p = gb.prob[i];
@@ -582,6 +587,7 @@ int enqueue_ggs(Context* ctx, pdb_matches* const* problems, int batch, int frame
       p.pose = pose_dev + (size_t)(b0 + i) * N * 9;
       p.xch1 = reinterpret_cast<unsigned long long*>(ws);
       p.xch2 = p.xch1 + 2 * (size_t)P.ctas_per_problem * ggs_xch_words(m->frames);
+      p.acc = reinterpret_cast<float*>(ws + ggs_ws_slots_bytes(max_frames, P.ctas_per_problem, P.xch_group));
       p.stats = stats_dev ? stats_dev + (b0 + i) : nullptr;
       p.dbg_clock = (ctx->ggs_clock && !ctx->den_clock && batch == 1) ? ctx->ggs_clock : nullptr;
       ws += ggs_ws_per_problem(max_frames, P.ctas_per_problem, P.xch_group);
@@ -615,6 +621,7 @@ int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_de
   PDB_CUDA(ctx, cudaSetDevice(ctx->device));
   GgsParams P = {};
   ggs_plan(ctx, 1, m->rounds > 0 ? m->rounds : 1, &P.ctas_per_problem, &P.xch_group);
+  P.xch_mode = ggs_xch_mode();
   const size_t ws_need = ggs_ws_per_problem(m->frames, P.ctas_per_problem, P.xch_group);
   if (int rc = ensure_buffer(ctx, &ctx->ggs_ws, &ctx->ggs_ws_bytes, ws_need)) return rc;
   PDB_CUDA(ctx, cudaMemsetAsync(ctx->ggs_ws, 0, ws_need, st));
@@ -641,6 +648,7 @@ int pdb_sampson_eval(pdb_context* c, const pdb_matches* pm, const float* pose_de
   p.pose = const_cast<float*>(pose_dev);  // eval mode never writes the pose
   p.xch1 = reinterpret_cast<unsigned long long*>(ws);
   p.xch2 = p.xch1 + 2 * (size_t)P.ctas_per_problem * ggs_xch_words(m->frames);
+  p.acc = reinterpret_cast<float*>(ws + ggs_ws_slots_bytes(m->frames, P.ctas_per_problem, P.xch_group));
   p.dbg_grad = grad_dev;
   p.dbg_scalars = scalars_dev;
   p.dbg_F = F_dev;

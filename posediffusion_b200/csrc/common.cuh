@@ -82,6 +82,29 @@ inline void st_ll(unsigned long long* p, unsigned bits, unsigned tag) {
   __atomic_store_n(p, ((unsigned long long)tag << 32) | (unsigned long long)bits, __ATOMIC_RELAXED);
 }
 inline unsigned long long ld_ll(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+// {fp32 sum, fp32 arrivals} accumulators of the one-hop all-reduce: the pair is updated / read as ONE 64-bit unit here
+inline void red_pair_add(float* p, float v) {
+  unsigned long long* u = reinterpret_cast<unsigned long long*>(p);
+  unsigned long long old = __atomic_load_n(u, __ATOMIC_RELAXED);
+  for (;;) {
+    float f[2];
+    memcpy(f, &old, 8);
+    f[0] += v;
+    f[1] += 1.0f;
+    unsigned long long want;
+    memcpy(&want, f, 8);
+    if (__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return;
+  }
+}
+inline float2 ld_pair(const float* p) {
+  const unsigned long long w = __atomic_load_n(reinterpret_cast<const unsigned long long*>(p), __ATOMIC_RELAXED);
+  float f[2];
+  memcpy(f, &w, 8);
+  return make_float2(f[0], f[1]);
+}
+inline void st_pair_zero(float* p) { __atomic_store_n(reinterpret_cast<unsigned long long*>(p), 0ull, __ATOMIC_RELAXED); }
+inline void red_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline void fence_gpu() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void ll_backoff() {  // the poller waits for other CTAs (OS threads): let the CTA's other threads publish first
   emu::yield();
   sched_yield();
@@ -125,6 +148,25 @@ __device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p)
   return w;
 }
 __device__ __forceinline__ void ll_backoff() {}
+// One-hop all-reduce accumulators: {fp32 sum, fp32 arrivals} in one 8-byte word.  ONE vector reduction adds {v, 1.0} to the
+// pair (red.v2.f32, sm_90+); a reader that sees the expected number of arrivals has the complete sum.  PTX only promises
+// per-element atomicity of a vector reduction; on this hardware both elements of the 8-byte-aligned pair are applied by the
+// L2 reduction unit in one pass (tools/xchg_probe.cu mode 8 watches for torn pairs: none in 4e8 polls, see profiles/).
+__device__ __forceinline__ void red_pair_add(float* p, float v) {
+  asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v), "f"(1.0f) : "memory");
+}
+__device__ __forceinline__ float2 ld_pair(const float* p) {
+  float2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_pair_zero(float* p) {
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(0ull) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void fence_gpu() { __threadfence(); }
 
 // mbarrier + bulk asynchronous copy (global -> shared, completion counted in bytes on an mbarrier)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

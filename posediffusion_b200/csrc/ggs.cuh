@@ -49,6 +49,7 @@ struct GgsProblem {
   float* pose;          // [frames*9] in/out
   unsigned long long* xch1;  // [2][ctas_per_problem][frames*7 + kAccTail] exchange slots of the CTAs, zero on entry
   unsigned long long* xch2;  // [2][groups][frames*7 + kAccTail] exchange slots of the group leaders, zero on entry
+  float* acc;                // one-hop exchange: [3][frames*7 + kAccTail][kAccStride] {sum, arrivals} accumulators, zero on entry
   pdb_ggs_stats* stats; // may be null
   float* dbg_grad;      // eval mode: [frames*9]
   float* dbg_scalars;   // eval mode: [4]
@@ -67,7 +68,9 @@ struct GgsParams {
   int resident_rounds;  // rounds of 32 matches that fit the CTA's shared-memory match cache (0 = always stream)
   int ring;             // 1: shared memory holds the bulk-async streaming ring (used when the slice is not resident)
   int xch_group;        // CTAs per exchange group; >= ctas_per_problem: one-level exchange (every CTA reads every slot)
+  int xch_mode;         // 0: flag-carrying words through slots (xch1 / xch2); 1: one hop through vector reductions (acc)
 };
+constexpr int kAccStride = 8;  // floats between two accumulators: one 32-byte sector each (spreads the L2 reduction units)
 
 __host__ __device__ inline int ggs_xch_words(int frames) { return frames * 7 + kAccTail; }
 __host__ __device__ inline int ggs_xch_groups(int cpp, int group) { return group >= cpp ? 0 : (cpp + group - 1) / group; }
@@ -131,11 +134,53 @@ __device__ __forceinline__ void sampson_match2_unit(const float4 X, const float4
 // s_gsum holds the sums -- the same bits in every CTA -- once the caller has passed a block barrier.  Kept out of line: its
 // 16-loads-in-flight polling loops would otherwise compete for registers with the streaming loop of stage 1.
 template <bool kEval>
-__device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned long long* xch2, int cpp, int cta, int group, int N,
-                                          unsigned it_global, const float* s_part, const float* s_misc, int cta_cnt, float g_fx,
+__device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned long long* xch2, float* accbase, int cpp, int cta, int group,
+                                          int N, unsigned it_global, const float* s_part, const float* s_misc, int cta_cnt, float g_fx,
                                           float g_fy, float* s_gsum) {
   const int tid = threadIdx.x;
   const int nsum = ggs_xch_words(N);
+  if (accbase) {
+    // ONE hop: every CTA adds {value, 1} to each accumulator (zeros for the frames it does not touch, so that every accumulator
+    // expects exactly `cpp` arrivals); the valid count travels as a packed 64-bit integer {arrivals : count}.  Everybody polls
+    // until the arrivals are complete.  Three buffers rotate; CTA 0 clears the one used by the previous iteration -- every CTA
+    // has read it (they all contributed to this iteration afterwards) and nobody adds to it before two more exchanges.
+    float* acc = accbase + (size_t)(it_global % 3u) * nsum * kAccStride;
+    for (int e = tid; e < nsum; e += kGgsThreads) {
+      float* slot = acc + (size_t)e * kAccStride;
+      if (e < N * 7) red_pair_add(slot, s_part[e]);
+      else if (e == N * 7 + 0) red_pair_add(slot, g_fx);
+      else if (e == N * 7 + 1) red_pair_add(slot, g_fy);
+      else if (e == N * 7 + 2) red_pair_add(slot, s_misc[4]);
+      else if (e == N * 7 + 3) red_pair_add(slot, kEval ? s_misc[5] : 0.f);
+      else red_add_u64(reinterpret_cast<unsigned long long*>(slot), (1ull << 32) | (unsigned long long)(unsigned)cta_cnt);
+    }
+    for (int e = tid; e < nsum; e += kGgsThreads) {
+      const float* slot = acc + (size_t)e * kAccStride;
+      if (e < nsum - 1) {
+        float2 v;
+        for (;;) {
+          v = ld_pair(slot);
+          if (v.y == (float)cpp) break;
+          ll_backoff();
+        }
+        s_gsum[e] = v.x;
+      } else {
+        unsigned long long w;
+        for (;;) {
+          w = ld_ll(reinterpret_cast<const unsigned long long*>(slot));
+          if ((unsigned)(w >> 32) == (unsigned)cpp) break;
+          ll_backoff();
+        }
+        s_gsum[e] = __uint_as_float((unsigned)w);
+      }
+    }
+    if (cta == 0) {
+      float* old = accbase + (size_t)((it_global + 2u) % 3u) * nsum * kAccStride;
+      for (int e = tid; e < nsum; e += kGgsThreads) st_pair_zero(old + (size_t)e * kAccStride);
+      fence_gpu();  // the zeros are in place before this CTA's next contribution can be observed
+    }
+    return;
+  }
   const unsigned tag = it_global + 1u;
   const size_t buf = it_global & 1u;
   unsigned long long* mine = xch1 + (buf * (size_t)cpp + (size_t)cta) * nsum;
@@ -314,6 +359,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   __syncthreads();
   frames_forward();
 
+  __shared__ long long clk_sum[8];  // probe (thread 0): {-, stage 1, stage 2b, exchange, stage 2a, iterations, stage 3 + 0, -}
+  if (tid < 8) clk_sum[tid] = 0;
   for (int phase = 0; phase < P.n_phases; ++phase) {
     const int flags = P.flags[phase];
     const bool upd_R = flags & 1, upd_T = flags & 2, upd_FL = flags & 4;
@@ -321,7 +368,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
     int done = 0, dropped = 0, last_valid = 0;          // tracked by warp 0
     float last_logged = __int_as_float(0x7fc00000);
     for (int iter = 0; iter < iters; ++iter) {
-      long long ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0;
+      long long ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck1a = 0;  // stage timing probe (thread 0; the sums are flushed once per launch)
       if (pr.dbg_clock && tid == 0) ck0 = clock64();
       // ================= chunks of <= kGgsMaxSeg pair segments (one chunk in all practical cases) =================
       for (int cs = seg_lo; cs <= seg_hi; cs += kGgsMaxSeg) {
@@ -580,6 +627,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
           }
         }
         __syncthreads();
+        if (pr.dbg_clock && tid == 0) ck1a = clock64();
         // ---- stage 2a: per-pair adjoint, one warp per segment, 18 lanes x 2 outputs; leaves the slots zeroed ----
         for (int sl = warp; sl < nchunk; sl += kGgsWarps) {
           const int4 sd = s_seg[sl];
@@ -638,14 +686,13 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       __syncthreads();
       if (pr.dbg_clock && tid == 0) ck2 = clock64();
       // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
-      ggs_exchange<kEval>(pr.xch1, pr.xch2, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
+      ggs_exchange<kEval>(pr.xch1, pr.xch2, P.xch_mode == 1 ? pr.acc : nullptr, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
                           (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum);
       ++it_global;
       __syncthreads();
       if (pr.dbg_clock && tid == 0) {
         ck3 = clock64();
-        long long* c = pr.dbg_clock + (size_t)cta * 8;
-        c[1] += ck1 - ck0; c[2] += ck2 - ck1; c[3] += ck3 - ck2; c[5] += 1;
+        clk_sum[1] += ck1a - ck0; clk_sum[4] += ck1 - ck1a; clk_sum[2] += ck2 - ck1; clk_sum[3] += ck3 - ck2; clk_sum[5] += 1;
       }
       // ================= stage 3: finish the step, all threads (identical in every CTA) =================
       bool drop_phase = false;
@@ -719,7 +766,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
           }
         }
       }
-      if (pr.dbg_clock && tid == 0) pr.dbg_clock[(size_t)cta * 8 + 6] += clock64() - ck3;
+      if (pr.dbg_clock && tid == 0) clk_sum[6] += clock64() - ck3;
       if (kEval) break;
       if (drop_phase) break;  // uniform: phase dropped on "insufficient valid matches" (no update, :103-108)
     }
@@ -731,6 +778,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       pr.stats->n_valid[phase] = last_valid;
     }
   }
+  if (pr.dbg_clock && tid == 0)
+    for (int k = 0; k < 8; ++k) pr.dbg_clock[(size_t)cta * 8 + k] += clk_sum[k];
   if (!kEval && cta == 0) {
     for (int e = tid; e < N9; e += kGgsThreads) pr.pose[e] = s_pose[e];
   }

@@ -119,6 +119,8 @@ extern "C" int ggs_emu_run(const float* pts, const int* segs /*[nseg+1][4] incl.
   pr.pose = pose;
   pr.xch1 = xch.data();
   pr.xch2 = xch.data() + 2 * (size_t)cpp * ggs_xch_words(frames);
+  std::vector<unsigned long long> acc(3 * (size_t)ggs_xch_words(frames) * kAccStride / 2 + 8, 0ull);  // 8-byte aligned accumulators
+  pr.acc = reinterpret_cast<float*>(acc.data());
   pr.stats = stats;
   pr.dbg_grad = dbg_grad;
   pr.dbg_scalars = dbg_scalars;
@@ -137,6 +139,7 @@ extern "C" int ggs_emu_run(const float* pts, const int* segs /*[nseg+1][4] incl.
   P.momentum = momentum;
   P.min_matches = min_matches;
   P.xch_group = group;
+  P.xch_mode = (getenv("PDB_GGS_XCH") && atoi(getenv("PDB_GGS_XCH")) == 0) ? 0 : 1;
   // the launch logic of api_core.cu::launch_ggs_chunk: shared-memory-resident slice when it fits, else the bulk-async ring
   const size_t fixed = ggs_smem_fixed_bytes(frames);
   const size_t budget = emu::kSharedBytes > fixed + 1024 ? emu::kSharedBytes - fixed - 1024 : 0;

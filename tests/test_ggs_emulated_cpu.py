@@ -149,13 +149,14 @@ def test_emulated_layouts_agree_on_ragged_and_tiny_segments(emu, mode, cpp):
 
 
 @pytest.mark.parametrize("layout", ["plain", "paired"])
-@pytest.mark.parametrize("cpp,group", [(5, 2), (7, 3), (6, 6)])
-def test_emulated_two_level_exchange(emu, layout, cpp, group, monkeypatch):
-    """The per-iteration all-reduce through flag-carrying exchange words (csrc/common.cuh st_ll / ll_sum): groups of `group`
-    CTAs with a ragged last group (two levels), or every CTA reading every slot (group == cpp).  Same fixtures and tolerances
-    as the one-level runs above; the exchange sums in a fixed order, so CTA counts that split the matches identically must
-    give bit-identical poses whatever the grouping."""
+@pytest.mark.parametrize("cpp,group,xch", [(5, 2, 0), (7, 3, 0), (6, 6, 0), (7, 3, 1)])
+def test_emulated_exchange_modes(emu, layout, cpp, group, xch, monkeypatch):
+    """The per-iteration all-reduce of the partial gradients.  xch = 0: flag-carrying exchange words (csrc/common.cuh st_ll /
+    ll_sum) -- groups of `group` CTAs with a ragged last group (two levels), or every CTA reading every slot (group == cpp);
+    xch = 1 (the default everywhere else in this file): one hop through {sum, arrivals} vector reductions.  Same fixtures and
+    tolerances as the runs above."""
     monkeypatch.setenv("PDB_GGS_GROUP", str(group))
+    monkeypatch.setenv("PDB_GGS_XCH", str(xch))
     g = load_golden("ggs.npz")
     cfg = syn.default_ggs_cfg()
     cfg["iter_num"] = int(g["iter_num"])

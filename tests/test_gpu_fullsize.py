@@ -116,9 +116,18 @@ def test_ggs_five_phases_vs_oracle_at_config3_size(ctx, dev, cfg3_scene, layout)
 def test_full_loop_ggs_on_teacher_forced_on_oracle_trajectory(dev):
     """T = 100, N = 20, GGS on with the default 700 inner iterations per guided step.  The oracle runs the whole loop on the
     CPU (small match set so that its 7 000 inner iterations finish in seconds); every one of the 100 steps of the CUDA path is
-    then started from the oracle's state and compared with the oracle's next state."""
+    then started from the oracle's state and compared with the oracle's next state.
+
+    Operating point: with random weights the sampler's trajectory has nothing to do with any scene, the guided steps then see a
+    handful of borderline-valid matches and 700 clipped SGD steps amplify one validity flip into percent-level differences
+    (measured 4.8e-2, round 2) -- in the reference as much as here.  The test therefore puts the loop where a trained model
+    would put it: the output layer of the (otherwise random) denoiser is scaled by 0.02, so the unguided dynamics are nearly
+    linear, x_{t-1} ~ k_t x_t, and x_T is chosen such that the state entering the first guided step is the perturbed
+    ground-truth pose of a geometry-consistent scene (most matches valid, as in test_ggs_long_run_vs_oracle)."""
     frames = 20
     state = syn.random_denoiser_state(5, 0.05)
+    state["_last.3.weight"] = state["_last.3.weight"] * 0.02
+    state["_last.3.bias"] = state["_last.3.bias"] * 0.02
     den = pdb.Denoiser(TRANSFORMER=TRANSFORMER)
     den.load_state_dict(state, strict=True)
     dif = pdb.GaussianDiffusion()
@@ -128,12 +137,19 @@ def test_full_loop_ggs_on_teacher_forced_on_oracle_trajectory(dev):
     sched = po.diffusion_schedule()
     m, gt, start = syn.scene_matches(frames, 24, seed=31)
     cfg = syn.default_ggs_cfg()
-    cfg.update(min_matches=0, verbose=False)
+    cfg.update(verbose=False)
     z = syn.random_features(1, frames, 31)
-    draws = syn.predraw_noise(1, frames, seed=31)
+    gain = 1.0
+    for t in range(99, 9, -1):  # eps ~ 0: x_{t-1} = (c1_t a_t + c2_t) x_t
+        gain *= float(sched["posterior_mean_coef1"][t] * sched["sqrt_recip_alphas_cumprod"][t] + sched["posterior_mean_coef2"][t])
+    draws = 1e-3 * syn.predraw_noise(1, frames, seed=31)
+    draws[0] = torch.from_numpy(start)[None] / gain
     cond_o = partial(po.geometry_guided_sampling, matches_dict=m, GGS_cfg=cfg)
-    _, ref = po.p_sample_loop(net, sched, z, draws, cond_o, 10)
+    log = []
+    _, ref = po.p_sample_loop(net, sched, z, draws, partial(po.geometry_guided_sampling, matches_dict=m, GGS_cfg=cfg, log=log), 10)
     assert torch.isfinite(ref).all()
+    assert all(e["iters"] in (100, 200) and not e["dropped"] for e in log) and len(log) == 50  # 10 guided steps x 5 phases, no early exit
+    assert (ref[90][0] - torch.from_numpy(start)).abs().max().item() < 0.5  # the guided steps start near the scene
     cond = partial(pdb.geometry_guided_sampling, matches_dict=m, GGS_cfg=cfg)
     zd = z.to(dev)
     worst_unguided = worst_guided = 0.0

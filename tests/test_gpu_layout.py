@@ -94,7 +94,10 @@ def test_sampson_eval_paired_seeded_sizes(ctx, dev, frames, per_pair, ragged, fo
     np.testing.assert_allclose(s1[:3].cpu().numpy(), s0[:3].cpu().numpy(), rtol=2e-5)
     c = s64.sampson_closed_form_f64(start, m)
     assert abs(int(s1[1].item()) - c["n_valid"]) <= 2
-    np.testing.assert_allclose(g1.cpu().numpy(), c["grad"], rtol=0, atol=3e-4 * np.abs(c["grad"]).max())
+    # fp32 is the limit at the config-3 size (778 240 matches): the reference's own fp32 operator sequence is 3.3e-4 * max|grad| away
+    # from float64 there (tests/test_gpu_fullsize.py states the measurement)
+    tol = 1e-3 if len(m["kp1"]) > 500000 else 3e-4
+    np.testing.assert_allclose(g1.cpu().numpy(), c["grad"], rtol=0, atol=tol * np.abs(c["grad"]).max())
 
 
 def test_paired_single_match_segments_and_register_stream_walk(ctx, dev, monkeypatch):

@@ -7,6 +7,8 @@
 //   mode 4  hop calibration (two CTAs bounce one word)
 //   mode 6  two levels with 16-byte {3 values, tag} words (counts torn words)
 //   mode 7  mode 2 with 16 loads in flight per thread (the kernel's setting)
+//   mode 8  ONE hop: red.v2.f32 {value, 1.0} into per-value accumulators, poll the arrival count (checks vector atomicity)
+//   mode 9  mode 7 + nanosleep back-off;  mode 10  poll one word per slot first, then read;  mode 11  three hops, minimal traffic
 //   mode 2  LL, TWO levels: groups of S CTAs, the group leader sums its group's slots and publishes a group slot,
 //           every CTA then reads the G group slots
 //
@@ -77,6 +79,15 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void red_v2(float* p, float a, float b) {
+  asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ld_f2(const float* p) {
+  float2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
 struct Params {
   int mode, words, iters, S, G, replicas;
   float* acc;                 // mode 0: [3][words*32]
@@ -89,6 +100,9 @@ struct Params {
   float4* vec1;               // mode 6: [2][ctas][words/3+1]
   float4* vec2;               // mode 6: [2][G][words/3+1]
   unsigned* torn;             // mode 6: count of torn 16-byte words observed
+  float* acc2;                // mode 8: [3][words][stride floats] {sum, arrivals}
+  int stride;                 // mode 8: floats between two accumulators (8 = 32 B, 32 = 128 B)
+  int backoff;                // modes 9: nanoseconds between poll retries
   float* out;                 // [ctas] checksum
   long long* cycles;          // [ctas]
 };
@@ -223,6 +237,97 @@ __global__ void __launch_bounds__(512, 1) xchg_kernel(const Params P) {
         s_sum[3 * e] = a.x;
         if (3 * e + 1 < P.words) s_sum[3 * e + 1] = a.y;
         if (3 * e + 2 < P.words) s_sum[3 * e + 2] = a.z;
+      }
+      __syncthreads();
+    } else if (P.mode == 8) {
+      // ONE hop: every CTA adds {value, 1.0} to each accumulator with one vector reduction (red.v2.f32); everybody polls the
+      // accumulators until the arrival count is complete.  Triple-buffered; CTA 0 zeroes the buffer used two iterations ago.
+      // The value added is exactly 1.0 here, so a consistent {sum, arrivals} pair always has sum == arrivals: any other
+      // observation means the two elements of the vector reduction were applied separately (counted in `torn`).
+      float* acc = P.acc2 + (size_t)(it % 3) * P.words * P.stride;
+      for (int e = tid; e < P.words; e += blockDim.x) red_v2(acc + (size_t)e * P.stride, 1.0f, 1.0f);
+      for (int e = tid; e < P.words; e += blockDim.x) {
+        float2 v;
+        do {
+          v = ld_f2(acc + (size_t)e * P.stride);
+          if (v.x != v.y) atomicAdd(P.torn, 1u);
+        } while (v.y != (float)C);
+        s_sum[e] = v.x;
+      }
+      if (cta == 0) {
+        float* old = P.acc2 + (size_t)((it + 2) % 3) * P.words * P.stride;
+        for (int e = tid; e < P.words; e += blockDim.x) *reinterpret_cast<float2*>(old + (size_t)e * P.stride) = make_float2(0.f, 0.f);
+        __threadfence();
+      }
+      __syncthreads();
+    } else if (P.mode == 9 || P.mode == 10) {
+      // mode 9: mode 7 + nanosleep between poll retries; mode 10: lanes of warp 0 first poll the LAST word of every slot
+      // (one load per slot per retry), then everybody reads (and verifies) the slots once
+      const int S = P.S, G = P.G;
+      unsigned long long* mys = P.slot1 + ((size_t)(it & 1) * C + cta) * P.words;
+      for (int e = tid; e < P.words; e += blockDim.x) st_ll(mys + e, contrib, tag);
+      const int g = cta / S;
+      auto sum_slots = [&](const unsigned long long* base, int count, int e) {
+        float sum = 0.f;
+        unsigned long long w[16];
+        bool ok;
+        do {
+          ok = true;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            w[k] = ld_ll(base + (size_t)min(k, count - 1) * P.words + e);
+            ok = ok && ((unsigned)(w[k] >> 32) == tag);
+          }
+          if (!ok && P.backoff) __nanosleep(P.backoff);
+        } while (!ok);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sum += (k < count) ? __uint_as_float((unsigned)w[k]) : 0.f;
+        return sum;
+      };
+      auto wait_last_word = [&](const unsigned long long* base, int count) {
+        if (tid < 32) {
+          bool ok;
+          do {
+            ok = true;
+            for (int k = tid; k < count; k += 32) ok = ok && ((unsigned)(ld_ll(base + (size_t)k * P.words + P.words - 1) >> 32) == tag);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok && P.backoff) __nanosleep(P.backoff);
+          } while (!ok);
+        }
+        __syncthreads();
+      };
+      if (cta % S == 0) {
+        const int c_lo = g * S, c_n = min(C, c_lo + S) - c_lo;
+        const unsigned long long* base = P.slot1 + ((size_t)(it & 1) * C + c_lo) * P.words;
+        if (P.mode == 10) wait_last_word(base, c_n);
+        for (int e = tid; e < P.words; e += blockDim.x)
+          st_ll(P.slot2 + ((size_t)(it & 1) * G + g) * P.words + e, sum_slots(base, c_n, e), tag);
+      }
+      const unsigned long long* base2 = P.slot2 + (size_t)(it & 1) * G * P.words;
+      if (P.mode == 10) wait_last_word(base2, G);
+      for (int e = tid; e < P.words; e += blockDim.x) s_sum[e] = sum_slots(base2, G, e);
+      __syncthreads();
+    } else if (P.mode == 11) {
+      // THREE hops, minimal traffic: members -> group leader -> all leaders sum the G group slots -> each leader publishes the
+      // total in its group's result slot -> members read ONE slot (12 readers per slot instead of 148 readers per group slot)
+      const int S = P.S, G = P.G;
+      unsigned long long* mys = P.slot1 + ((size_t)(it & 1) * C + cta) * P.words;
+      for (int e = tid; e < P.words; e += blockDim.x) st_ll(mys + e, contrib, tag);
+      const int g = cta / S;
+      unsigned long long* result = P.slot2 + ((size_t)(2 + (it & 1)) * G + g) * P.words;  // second half of slot2: result slots
+      if (cta % S == 0) {
+        const int c_lo = g * S, c_n = min(C, c_lo + S) - c_lo;
+        const unsigned long long* base = P.slot1 + ((size_t)(it & 1) * C + c_lo) * P.words;
+        for (int e = tid; e < P.words; e += blockDim.x)
+          st_ll(P.slot2 + ((size_t)(it & 1) * G + g) * P.words + e, ll_sum_f<16>(base + e, P.words, c_n, tag), tag);
+        const unsigned long long* base2 = P.slot2 + (size_t)(it & 1) * G * P.words;
+        for (int e = tid; e < P.words; e += blockDim.x) {
+          const float total = ll_sum_f<16>(base2 + e, P.words, G, tag);
+          st_ll(result + e, total, tag);
+          s_sum[e] = total;
+        }
+      } else {
+        for (int e = tid; e < P.words; e += blockDim.x) s_sum[e] = ll_sum_f<16>(result + e, P.words, 1, tag);
       }
       __syncthreads();
     } else if (P.mode == 7) {
@@ -366,30 +471,36 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&P.vec1, sizeof(float4) * 2 * maxC * (words / 3 + 1)));
   CK(cudaMalloc(&P.vec2, sizeof(float4) * 2 * 64 * (words / 3 + 1)));
   CK(cudaMalloc(&P.torn, 256));
+  CK(cudaMalloc(&P.acc2, sizeof(float) * 3 * words * 32));
   CK(cudaMemset(P.torn, 0, 256));
   CK(cudaMalloc(&P.out, sizeof(float) * maxC));
   CK(cudaMalloc(&P.cycles, sizeof(long long) * maxC));
   CK(cudaFuncSetAttribute(xchg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   struct Case { int mode, C, S, rep; };
   std::vector<Case> cases;
-  cases.push_back({4, 2, 1, 1});
-  cases.push_back({4, 148, 1, 1});
+  // {mode, ctas, S, rep}; for mode 8 S = accumulator stride in floats; for mode 9/10 rep = nanosleep ns
   for (int C : {18, 74, 148}) {
     cases.push_back({0, C, 0, 1});
-    for (int S : {4, 6, 8, 10, 12, 14, 16})
-      if (S < C) {
-        cases.push_back({7, C, S, 1});
-        if (S == 8 || S == 12 || S == 16) {
-          cases.push_back({3, C, S, 1});
-          cases.push_back({6, C, S, 1});
-        }
-      }
+    cases.push_back({8, C, 8, 1});
+    cases.push_back({8, C, 32, 1});
+    for (int S : {10, 12}) {
+      if (S >= C) continue;
+      cases.push_back({7, C, S, 1});
+      cases.push_back({9, C, S, 100});
+      cases.push_back({9, C, S, 400});
+      cases.push_back({10, C, S, 0});
+      cases.push_back({10, C, S, 100});
+      cases.push_back({11, C, S, 1});
+    }
   }
   for (const Case& c : cases) {
     P.mode = c.mode;
     P.S = c.S;
     P.G = c.S ? (c.C + c.S - 1) / c.S : 0;
-    P.replicas = c.rep;
+    P.replicas = 1;
+    P.stride = c.S;
+    P.backoff = c.rep;
+    CK(cudaMemset(P.torn, 0, 256));
     CK(cudaMemset(P.acc, 0, sizeof(float) * 3 * words * 32));
     CK(cudaMemset(P.bar, 0, 256));
     CK(cudaMemset(P.slot1, 0, sizeof(unsigned long long) * 2 * maxC * words));
@@ -408,6 +519,7 @@ int main(int argc, char** argv) {
       CK(cudaMemset(P.flags, 0, sizeof(unsigned) * 2 * (maxC + 64) * 32));
       CK(cudaMemset(P.vec1, 0, sizeof(float4) * 2 * maxC * (words / 3 + 1)));
       CK(cudaMemset(P.vec2, 0, sizeof(float4) * 2 * 64 * (words / 3 + 1)));
+      CK(cudaMemset(P.acc2, 0, sizeof(float) * 3 * words * 32));
       CK(cudaEventRecord(a));
       CK(cudaLaunchCooperativeKernel((void*)xchg_kernel, dim3(c.C), dim3(512), args, 64 * 1024, 0));
       CK(cudaEventRecord(b));
