@@ -70,7 +70,8 @@ struct GgsParams {
   int xch_group;        // CTAs per exchange group; >= ctas_per_problem: one-level exchange (every CTA reads every slot)
   int xch_mode;         // 0: flag-carrying words through slots (xch1 / xch2); 1: one hop through vector reductions (acc)
 };
-constexpr int kAccStride = 8;  // floats between two accumulators: one 32-byte sector each (spreads the L2 reduction units)
+constexpr int kAccStride = 32;  // floats between two accumulators: one 128-byte line each (148 CTAs adding into neighbouring
+                                // sectors serialise on a few L2 slices: 3.4 us per all-reduce at 32 B, 2.2 us at 128 B, tools/xchg_probe.cu)
 
 __host__ __device__ inline int ggs_xch_words(int frames) { return frames * 7 + kAccTail; }
 __host__ __device__ inline int ggs_xch_groups(int cpp, int group) { return group >= cpp ? 0 : (cpp + group - 1) / group; }
