@@ -76,11 +76,12 @@ constexpr int kAccStride = 32;  // floats between two accumulators: one 128-byte
 __host__ __device__ inline int ggs_xch_words(int frames) { return frames * 7 + kAccTail; }
 __host__ __device__ inline int ggs_xch_groups(int cpp, int group) { return group >= cpp ? 0 : (cpp + group - 1) / group; }
 
-constexpr int kGgsFixedFloatsPerFrame = 3 * 9 + 4 * 9 + 8 + 18 + 14;  // pose x2, vel, R, A, Rt, At, (fl, inr) x2, gAt|gRt, partial + summed gradient
+constexpr int kGgsFixedFloatsPerFrame = 2 * 9 + 4 * 9 + 4 + 18 + 14;  // pose, vel, R, A, Rt, At, fl, inr, gAt|gRt, partial + summed gradient
 
 __host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
   size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 128 + (size_t)kGgsMaxSeg * kSegAcc);
   bytes += kGgsMaxSeg * sizeof(int);         // segment valid counts
+  bytes += 2 * (size_t)frames * sizeof(int);  // exchange plan: contributors per frame, own frames
   bytes += (kGgsMaxSeg + 1) * sizeof(int4);  // segment descriptors
   return (bytes + 127) / 128 * 128;
 }
@@ -137,19 +138,20 @@ __device__ __forceinline__ void sampson_match2_unit(const float4 X, const float4
 template <bool kEval>
 __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned long long* xch2, float* accbase, int cpp, int cta, int group,
                                           int N, unsigned it_global, const float* s_part, const float* s_misc, int cta_cnt, float g_fx,
-                                          float g_fy, float* s_gsum) {
+                                          float g_fy, float* s_gsum, const int* s_expect, const int* s_mine) {
   const int tid = threadIdx.x;
   const int nsum = ggs_xch_words(N);
   if (accbase) {
-    // ONE hop: every CTA adds {value, 1} to each accumulator (zeros for the frames it does not touch, so that every accumulator
-    // expects exactly `cpp` arrivals); the valid count travels as a packed 64-bit integer {arrivals : count}.  Everybody polls
-    // until the arrivals are complete.  Three buffers rotate; CTA 0 clears the one used by the previous iteration -- every CTA
+    // ONE hop: a CTA adds {value, 1} to the accumulators of the frames its segments touch (s_mine; zeros if the gradient of a
+    // touched frame happens to vanish) and to the five scalars; an accumulator of frame n expects s_expect[n] arrivals, a scalar
+    // `cpp`.  The valid count travels as a packed 64-bit integer {arrivals : count}.  Everybody polls until the arrivals are complete.  Three buffers rotate; CTA 0 clears the one used by the previous iteration -- every CTA
     // has read it (they all contributed to this iteration afterwards) and nobody adds to it before two more exchanges.
     float* acc = accbase + (size_t)(it_global % 3u) * nsum * kAccStride;
     for (int e = tid; e < nsum; e += kGgsThreads) {
       float* slot = acc + (size_t)e * kAccStride;
-      if (e < N * 7) red_pair_add(slot, s_part[e]);
-      else if (e == N * 7 + 0) red_pair_add(slot, g_fx);
+      if (e < N * 7) {
+        if (s_mine[e / 7]) red_pair_add(slot, s_part[e]);
+      } else if (e == N * 7 + 0) red_pair_add(slot, g_fx);
       else if (e == N * 7 + 1) red_pair_add(slot, g_fy);
       else if (e == N * 7 + 2) red_pair_add(slot, s_misc[4]);
       else if (e == N * 7 + 3) red_pair_add(slot, kEval ? s_misc[5] : 0.f);
@@ -158,10 +160,11 @@ __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned lon
     for (int e = tid; e < nsum; e += kGgsThreads) {
       const float* slot = acc + (size_t)e * kAccStride;
       if (e < nsum - 1) {
+        const float want = (float)(e < N * 7 ? s_expect[e / 7] : cpp);
         float2 v;
         for (;;) {
           v = ld_pair(slot);
-          if (v.y == (float)cpp) break;
+          if (v.y == want) break;
           ll_backoff();
         }
         s_gsum[e] = v.x;
@@ -233,25 +236,22 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
 
   // ---- shared memory carve-up ----
   int4* s_seg = reinterpret_cast<int4*>(smem_raw);
-  // pose, focal length and clamp mask are double buffered: stage 3 writes the updated pose into the other buffer while
-  // slower warps still read the current one for the clip norms (saves a block barrier per iteration)
-  float* s_pose = reinterpret_cast<float*>(s_seg + kGgsMaxSeg + 1);  // current pose
-  float* s_pose_nxt = s_pose + N9;
-  float* s_vel = s_pose_nxt + N9;
+  float* s_pose = reinterpret_cast<float*>(s_seg + kGgsMaxSeg + 1);
+  float* s_vel = s_pose + N9;
   float* s_R = s_vel + N9;
   float* s_A = s_R + N9;
   float* s_Rt = s_A + N9;
   float* s_At = s_Rt + N9;
-  float* s_fl = s_At + N9;          // current clamped focal lengths [N][2]
+  float* s_fl = s_At + N9;          // clamped focal lengths [N][2]
   float* s_inr = s_fl + 2 * N;      // 1 where the clamp passes gradient
-  float* s_fl_nxt = s_inr + 2 * N;
-  float* s_inr_nxt = s_fl_nxt + 2 * N;
-  float* s_fg = s_inr_nxt + 2 * N;  // [N][18]: gAt (0..8), gRt (9..17)
-  float* s_misc = s_fg + 2 * N9;    // [4] clamp_sum, [5] loss_sum, [8..11] sum over frames of d/d(ix, iy, kx, ky)
+  float* s_fg = s_inr + 2 * N;      // [N][18]: gAt (0..8), gRt (9..17)
+  float* s_misc = s_fg + 2 * N9;    // [4] clamp_sum, [5] loss_sum, [8..11] sum over frames of d/d(ix, iy, kx, ky), [16..47] norm partials
   float* s_part = s_misc + 64;      // [N*7] this CTA's partial gradient of the iteration
   float* s_gsum = s_part + N * 7 + 32;  // [N*7 + kAccTail] summed gradient of this iteration (all CTAs: identical bits)
   float* s_sacc = s_gsum + N * 7 + 32;  // [kGgsMaxSeg][kSegAcc]
   int* s_scnt = reinterpret_cast<int*>(s_sacc + kGgsMaxSeg * kSegAcc);
+  int* s_expect = s_scnt + kGgsMaxSeg;  // [N] CTAs of this sequence that contribute to frame n (one-hop exchange)
+  int* s_mine = s_expect + N;           // [N] 1 if this CTA's segments touch frame n
   float4* s_pts = reinterpret_cast<float4*>(smem_raw + ggs_smem_fixed_bytes(N));
   __shared__ int s_cta_cnt;
 
@@ -300,6 +300,31 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
     const int count = (r_cta1 - r_cta0) * 32;
     for (int e = tid; e < count; e += kGgsThreads) s_pts[e] = ld_stream_f4(src + e);
   }
+  // ---- exchange plan (static): a CTA only adds to the accumulators of the frames its pair segments touch, and every CTA knows
+  // how many contributions each frame's accumulators will receive (thread c replays the partition of CTA c)
+  for (int e = tid; e < 2 * N; e += kGgsThreads) s_expect[e] = 0;  // s_expect and s_mine are adjacent
+  __syncthreads();
+  for (int c = tid; c < cpp; c += kGgsThreads) {
+    int a0, a1;
+    ggs_cta_range(R, c, cpp, kPaired, &a0, &a1);
+    if (a1 > a0) {
+      const int lo = seg_of_round(a0), hi = seg_of_round(a1 - 1);
+      unsigned long long m_lo = 0ull, m_hi = 0ull;  // kMaxFrames = 128 frame bits
+      for (int sg = lo; sg <= hi; ++sg) {
+        const int4 d = __ldg(&pr.segs[sg]);
+        if (d.z < 64) m_lo |= 1ull << d.z; else m_hi |= 1ull << (d.z - 64);
+        if (d.w < 64) m_lo |= 1ull << d.w; else m_hi |= 1ull << (d.w - 64);
+      }
+      for (int n = 0; n < N; ++n) {
+        const bool on = (n < 64 ? (m_lo >> n) : (m_hi >> (n - 64))) & 1ull;
+        if (on) {
+          atomicAdd(&s_expect[n], 1);
+          if (c == cta) s_mine[n] = 1;
+        }
+      }
+    }
+  }
+  static_assert(kMaxFrames <= 128, "frame bit masks of the exchange plan");
   const float scale = 0.5f * fminf(pr.height, pr.width);
   const float cx = 0.5f * pr.width, cy = 0.5f * pr.height;
   unsigned it_global = 0;
@@ -663,32 +688,44 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       __syncthreads();
       if (pr.dbg_clock && tid == 0) ck1 = clock64();
       // ================= stage 2b: one thread per frame: unfold K, frame adjoint -> the CTA's partial gradient =================
-      if (tid < N) {
+      if (warp * 32 < N) {  // the warps that hold frames (one thread per frame)
         const int n = tid;
-        float* gAt = s_fg + n * 18;
-        bool touched = false;
+        float k4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n < N) {
+          float* gAt = s_fg + n * 18;
+          bool touched = false;
 #pragma unroll
-        for (int k = 0; k < 18; ++k) touched |= (gAt[k] != 0.f);
-        float gT[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-        if (touched) {
-          float gA[9], gR[9], k4[4];
-          frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
-          frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
+          for (int k = 0; k < 18; ++k) touched |= (gAt[k] != 0.f);
+          float gT[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+          if (touched) {
+            float gA[9], gR[9];
+            frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
+            frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) atomicAdd(&s_misc[8 + k], k4[k]);
+            for (int k = 0; k < 18; ++k) gAt[k] = 0.f;
+          }
 #pragma unroll
-          for (int k = 0; k < 18; ++k) gAt[k] = 0.f;
+          for (int k = 0; k < 3; ++k) s_part[n * 7 + k] = gT[k];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) s_part[n * 7 + 3 + k] = gq[k];
         }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) s_part[n * 7 + k] = gT[k];
+        for (int k = 0; k < 4; ++k) k4[k] = warp_sum(k4[k]);  // d/d(ix, iy, kx, ky) summed over the warp's frames
+        if (lane == 0) {
+          if (N <= 32) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s_part[n * 7 + 3 + k] = gq[k];
+            for (int k = 0; k < 4; ++k) s_misc[8 + k] = k4[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(&s_misc[8 + k], k4[k]);
+          }
+        }
       }
       __syncthreads();
       if (pr.dbg_clock && tid == 0) ck2 = clock64();
       // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
       ggs_exchange<kEval>(pr.xch1, pr.xch2, P.xch_mode == 1 ? pr.acc : nullptr, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
-                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum);
+                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum, s_expect, s_mine);
       ++it_global;
       __syncthreads();
       if (pr.dbg_clock && tid == 0) {
@@ -733,35 +770,55 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               }
             }
           } else {
-            // clip norms: every warp reduces the whole gradient itself (lane-strided partial sums, xor butterfly): the same
-            // bits in every warp and every CTA, and no block barrier
+            // clip norms: one element per thread (N9 <= 1152: up to three), warp sums, partials through shared memory
+            constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
+            float gv[kPer];
             float gn2 = 0.f, pn2 = 0.f;
-            for (int e = lane; e < N9; e += 32) {
-              const float g1 = grad_of(e);
-              gn2 = fmaf(g1, g1, gn2);
-              const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
-              pn2 = fmaf(pm, pm, pn2);
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              gv[q] = 0.f;
+              if (e < N9) {
+                const float g1 = grad_of(e);
+                gv[q] = g1;
+                gn2 = fmaf(g1, g1, gn2);
+                const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
+                pn2 = fmaf(pm, pm, pn2);
+              }
             }
-            gn2 = warp_sum(gn2);
-            pn2 = warp_sum(pn2);
+            const int warps_used = min(kGgsWarps, (N9 + 31) / 32);  // warps that hold elements (the others contribute zeros)
+            if (warp < warps_used) {
+              gn2 = warp_sum(gn2);
+              pn2 = warp_sum(pn2);
+              if (lane == 0) {
+                s_misc[16 + warp * 2] = gn2;
+                s_misc[16 + warp * 2 + 1] = pn2;
+              }
+            }
+            __syncthreads();
+            gn2 = 0.f;
+            pn2 = 0.f;
+            for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
+              gn2 += s_misc[16 + wv * 2];
+              pn2 += s_misc[16 + wv * 2 + 1];
+            }
             const float max_norm = P.alpha * sqrtf(pn2) / P.lr;      // :119
             const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
             const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
-            for (int e = tid; e < N9; e += kGgsThreads) {
-              const float g1 = grad_of(e) * coef;
-              const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
-              s_vel[e] = v;
-              const float pnew = s_pose[e] - P.lr * v;
-              s_pose_nxt[e] = pnew;
-              const int n = e / 9, c = e - n * 9;
-              if (c >= 7) focal_of(pnew, &s_fl_nxt[n * 2 + (c - 7)], &s_inr_nxt[n * 2 + (c - 7)]);
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              if (e < N9) {
+                const float g1 = gv[q] * coef;
+                const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
+                s_vel[e] = v;
+                const float pnew = s_pose[e] - P.lr * v;
+                s_pose[e] = pnew;
+                const int n = e / 9, c = e - n * 9;
+                if (c >= 7) focal_of(pnew, &s_fl[n * 2 + (c - 7)], &s_inr[n * 2 + (c - 7)]);
+              }
             }
             ++done;
-            {  // the updated pose becomes the current one (uniform: every thread swaps its pointers)
-              float* t0 = s_pose; s_pose = s_pose_nxt; s_pose_nxt = t0;
-              float* t1 = s_fl; s_fl = s_fl_nxt; s_fl_nxt = t1;
-              float* t2 = s_inr; s_inr = s_inr_nxt; s_inr_nxt = t2;
-            }
             __syncthreads();
             frames_forward();  // stage 0 of the next iteration (one block barrier inside)
           }
