@@ -269,129 +269,6 @@ __device__ __forceinline__ void linear_item(const LinW<K>& W, const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// Second thread mapping of a linear work item (used when K/4 is a multiple of 64: K = 256, 512, 1024 -- every stage of the
-// per-step chain).  The first mapping gives every thread ONE output feature, so the 8 feature lanes of a k-slice read the same
-// activation float4: 80 LDS.128 per thread and item at K = 512, 8 warps x 80 x 4 shared-memory cycles = 2.5 k cycles per
-// item -- the stage was bound by shared-memory bandwidth, not by FMAs (tools/den_stage_probe.py: 2.5 k cycles per item).
-// Here a thread owns 4 features x TS/2 tokens of one k-slice out of 64:
-//   warp = (k half kh, token half th, feature quad fq), lane = k-slice within the half  ->  slice = kh*32 + lane
-//   k4-rows of the slice: i*64 + slice, i < K/256;  features o0 + fq*4 .. +3;  tokens th*TS/2 .. +TS/2-1
-// so an activation float4 is loaded once per 16 FMAs (LDS.128 per thread: K/256 * TS/2 = 20 at K = 512), a warp's load is 512
-// contiguous bytes, and the partial sums (2 TS per thread) are reduced over the 32 lanes with a halving butterfly
-// (2.25 TS shuffles) and over the two k halves through shared memory.
-// ---------------------------------------------------------------------------------------------
-template <int K>
-struct LinW2 {
-  static constexpr int K4 = K / 4;
-  static constexpr int PER = K4 / 64;
-  static_assert(K4 % 64 == 0 && PER >= 1 && PER <= 4, "K layout of the second mapping");
-  float4 w[PER][4];
-};
-
-template <int K>
-__device__ __forceinline__ void linear_prefetch2(LinW2<K>& W, const float4* __restrict__ Wp, int O, int o0) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slice = (warp >> 2) * 32 + lane, fq = warp & 1;
-  const float4* wp = Wp + (size_t)slice * O + o0 + fq * 4;
-#pragma unroll
-  for (int i = 0; i < LinW2<K>::PER; ++i)
-#pragma unroll
-    for (int f = 0; f < 4; ++f) W.w[i][f] = __ldg(wp + (size_t)i * 64 * O + f);
-}
-
-template <int TS, int K>
-__device__ __forceinline__ void linear_item2(const LinW2<K>& W, const float* __restrict__ Xs, float* __restrict__ red, int o0,
-                                             const float* __restrict__ bias, const float* __restrict__ add1, int ld1,
-                                             const float* __restrict__ add2, const float* __restrict__ add_row_scaled,
-                                             const float* __restrict__ row_scale, float* __restrict__ Y, int ldy, int row0,
-                                             int valid_end, int epi) {
-  static_assert(TS % 4 == 0 && TS <= 32, "token tile");
-  constexpr int TH = TS / 2;      // tokens per thread
-  constexpr int NV = 4 * TH;      // partial sums per thread, index f * TH + t
-  constexpr int PER = LinW2<K>::PER;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int kh = warp >> 2, th = (warp >> 1) & 1, fq = warp & 1;
-  // epilogue operands of this thread's output (token s_out, feature f_out) are requested before the FMA loop
-  const int s_out = threadIdx.x >> 3, f_out = threadIdx.x & 7;
-  const bool has_out = s_out < TS && (row0 + s_out) < valid_end;
-  float epi_add = 0.f;
-  if (has_out) {
-    const int row = row0 + s_out, o = o0 + f_out;
-    if (bias) epi_add += __ldg(bias + o);
-    if (add1) epi_add += __ldcg(add1 + (size_t)row * ld1 + o);
-    if (add2) epi_add += __ldg(add2 + o);
-    if (add_row_scaled) epi_add += __ldg(add_row_scaled + o) * row_scale[s_out];
-  }
-  float acc[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.f;
-  const float* xs = Xs + (size_t)(th * TH) * K + (kh * 32 + lane) * 4;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-#pragma unroll
-    for (int t = 0; t < TH; ++t) {
-      const float4 xv = *reinterpret_cast<const float4*>(xs + t * K + i * 256);
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        acc[f * TH + t] = fmaf(W.w[i][f].x, xv.x, fmaf(W.w[i][f].y, xv.y, fmaf(W.w[i][f].z, xv.z, fmaf(W.w[i][f].w, xv.w, acc[f * TH + t]))));
-    }
-  }
-  // reduce over the 32 k-slices of the warp: three halving steps (lane bits 4, 3, 2 select which part a lane keeps), then two
-  // full exchanges; afterwards the 4 lanes of a quad hold the same NV/8 sums, block index (lane >> 2)
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int v = 0; v < NV / 2; ++v) {
-      const float send = hi ? acc[v] : acc[v + NV / 2];
-      const float keep = hi ? acc[v + NV / 2] : acc[v];
-      acc[v] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-#pragma unroll
-    for (int v = 0; v < NV / 4; ++v) {
-      const float send = hi ? acc[v] : acc[v + NV / 4];
-      const float keep = hi ? acc[v + NV / 4] : acc[v];
-      acc[v] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int v = 0; v < NV / 8; ++v) {
-      const float send = hi ? acc[v] : acc[v + NV / 8];
-      const float keep = hi ? acc[v + NV / 8] : acc[v];
-      acc[v] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < NV / 8; ++v) {
-    acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 2);
-    acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 1);
-  }
-  // red[kh][th][fq][NV]: block b = lane >> 2 holds the sums v = b * NV/8 .. + NV/8 - 1
-  if ((lane & 3) == 0) {
-    float* dst = red + ((kh * 2 + th) * 2 + fq) * NV + (lane >> 2) * (NV / 8);
-#pragma unroll
-    for (int v = 0; v < NV / 8; ++v) dst[v] = acc[v];
-  }
-  __syncthreads();
-  if (s_out < TS) {
-    const int th_o = s_out / TH, t = s_out - th_o * TH, fq_o = f_out >> 2, f = f_out & 3;
-    const int v = f * TH + t;
-    float r = red[((0 * 2 + th_o) * 2 + fq_o) * NV + v] + red[((1 * 2 + th_o) * 2 + fq_o) * NV + v];
-    if (has_out) {
-      r += epi_add;
-      if (epi == kEpiRelu) r = fmaxf(r, 0.f);
-      else if (epi == kEpiSilu) r = r / (1.0f + expf(-r));
-      Y[(size_t)(row0 + s_out) * ldy + o0 + f_out] = r;
-    }
-  }
-  __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------
 // Self-attention for one (sequence, head): N <= 128 keys, head dim 128, fp32.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void attention_item(float* __restrict__ smem, const float* __restrict__ qkv,
@@ -406,28 +283,12 @@ __device__ __forceinline__ void attention_item(float* __restrict__ smem, const f
   const int i = chunk * kDenWarps + warp;  // this warp's query row
   float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < N) qv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)i * 3 * kDM) + lane);
-  // K and V of the head: ALL loads of a batch of 4 float4 pairs per thread are issued before the first is stored (one L2 round
-  // trip for N <= 32 instead of one per loop trip)
-  for (int e0 = threadIdx.x; e0 < N * (kHD / 4); e0 += 4 * kDenThreads) {
-    float4 kv[4], vv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * kDenThreads;
-      if (e < N * (kHD / 4)) {
-        const int j = e / (kHD / 4), d4 = e - j * (kHD / 4);
-        kv[u] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + kDM) + d4);
-        vv[u] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + 2 * kDM) + d4);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * kDenThreads;
-      if (e < N * (kHD / 4)) {
-        const int j = e / (kHD / 4), d4 = e - j * (kHD / 4);
-        *reinterpret_cast<float4*>(Ks + j * KP + d4 * 4) = kv[u];
-        *reinterpret_cast<float4*>(Vs + j * kHD + d4 * 4) = vv[u];
-      }
-    }
+  for (int e = threadIdx.x; e < N * (kHD / 4); e += kDenThreads) {
+    const int j = e / (kHD / 4), d4 = e - j * (kHD / 4);
+    const float4 kv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + kDM) + d4);
+    const float4 vv = __ldcg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * kDM + 2 * kDM) + d4);
+    *reinterpret_cast<float4*>(Ks + j * KP + d4 * 4) = kv;
+    *reinterpret_cast<float4*>(Vs + j * kHD + d4 * 4) = vv;
   }
   const float scaling = 0.08838834764831845f;  // 1/sqrt(128): q is scaled before QK^T (torch MHA)
   *reinterpret_cast<float4*>(Qs + warp * kHD + lane * 4) = make_float4(qv.x * scaling, qv.y * scaling, qv.z * scaling, qv.w * scaling);
@@ -562,22 +423,17 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
                           const float* add2, const float* add_rs, const float* rs, float* Y, int ldy, int epi,
                           bool need_barrier) {
     constexpr int K = decltype(ktag)::value;
-    constexpr bool kSecond = (K / 4) % 64 == 0;  // thread mapping of the item (see LinW2)
     const int groups = O / kFPI;
     const int n_items = tiles * groups;
-    typename std::conditional<kSecond, LinW2<kSecond ? K : 256>, LinW<K>>::type wreg;
-    auto prefetch = [&](int o0) {
-      if constexpr (kSecond) linear_prefetch2<K>(wreg, Wp, O, o0);
-      else linear_prefetch<K>(wreg, Wp, O, o0);
-    };
+    LinW<K> wreg;
     int item = blockIdx.x;
-    if (item < n_items) prefetch((item % groups) * kFPI);
+    if (item < n_items) linear_prefetch<K>(wreg, Wp, O, (item % groups) * kFPI);
     if (need_barrier) barrier();
     float* red = Xs + TS * K;
     int staged_tile = -1;  // the activations of a token tile are staged once and reused by this CTA's later items of the stage
     for (; item < n_items; item += G) {
       const int tt = item / groups, fg = item - tt * groups;
-      if (item != (int)blockIdx.x) prefetch(fg * kFPI);
+      if (item != (int)blockIdx.x) linear_prefetch<K>(wreg, Wp, O, fg * kFPI);
       long long c0 = 0, c1 = 0;
       if (probe) c0 = clock64();
       if (tt != staged_tile) {
@@ -586,10 +442,7 @@ denoiser_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ D
       }
       __syncthreads();
       if (probe) c1 = clock64();
-      if constexpr (kSecond)
-        linear_item2<TS, K>(wreg, Xs, red, fg * kFPI, bias, add1, ld1, add2, add_rs, rs, Y, ldy, tt * TS, S, epi);
-      else
-        linear_item<TS, K>(wreg, Xs, red, fg * kFPI, bias, add1, ld1, add2, add_rs, rs, Y, ldy, tt * TS, S, epi);
+      linear_item<TS, K>(wreg, Xs, red, fg * kFPI, bias, add1, ld1, add2, add_rs, rs, Y, ldy, tt * TS, S, epi);
       if (probe) {
         clk[1] += c1 - c0;
         clk[2] += clock64() - c1;
