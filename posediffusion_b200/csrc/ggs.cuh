@@ -327,6 +327,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   static_assert(kMaxFrames <= 128, "frame bit masks of the exchange plan");
   const float scale = 0.5f * fminf(pr.height, pr.width);
   const float cx = 0.5f * pr.width, cy = 0.5f * pr.height;
+  // per-launch constants of the step (the divisions are off the per-iteration dependency chain)
+  const float scale_over_N = scale / (float)N, inv_m_total = 1.0f / (float)pr.m_total, alpha_over_lr = P.alpha / P.lr;
   unsigned it_global = 0;
   float kin[4] = {0.f, 0.f, 0.f, 0.f}, fpx = 1.f, fpy = 1.f;  // shared intrinsics (every warp holds a copy)
 
@@ -345,12 +347,12 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         fx += s_fl[m * 2];
         fy += s_fl[m * 2 + 1];
       }
-      fpx = warp_sum(fx) / (float)N * scale;
-      fpy = warp_sum(fy) / (float)N * scale;
+      fpx = warp_sum(fx) * scale_over_N;
+      fpy = warp_sum(fy) * scale_over_N;
       kin[0] = 1.f / fpx;
       kin[1] = 1.f / fpy;
-      kin[2] = -cx / fpx;
-      kin[3] = -cy / fpy;
+      kin[2] = -cx * kin[0];
+      kin[3] = -cy * kin[1];
     }
     const int n = tid >> 2, j = tid & 3;
     if (n < N && j < 3) {
@@ -737,7 +739,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       {
         const int n_valid = __float_as_int(s_gsum[N * 7 + 4]);
         last_valid = n_valid;
-        last_logged = s_gsum[N * 7 + 2] / (float)pr.m_total;
+        last_logged = s_gsum[N * 7 + 2] * inv_m_total;
         // len(valid) / N < min_matches  (:103-105), evaluated as n < min_matches * N in float64
         drop_phase = !kEval && (P.min_matches > 0.0) && ((double)n_valid < P.min_matches * (double)N);
         if (tid == 0) {  // the CTA-level partial sums are consumed: zero them for the next iteration (written after >= 1 barrier)
@@ -749,8 +751,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
           dropped = 1;
         } else {
           const float inv_n = 1.0f / (float)n_valid;  // mean over the valid matches (:110)
-          const float gfx = upd_FL ? s_gsum[N * 7 + 0] * (scale / (float)N) : 0.f;
-          const float gfy = upd_FL ? s_gsum[N * 7 + 1] * (scale / (float)N) : 0.f;
+          const float gfx = upd_FL ? s_gsum[N * 7 + 0] * scale_over_N : 0.f;
+          const float gfy = upd_FL ? s_gsum[N * 7 + 1] * scale_over_N : 0.f;
           auto grad_of = [&](int e) {  // d mean(valid err) / d pose[e]
             const int n = e / 9, c = e - n * 9;
             float gsum;
@@ -802,7 +804,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               gn2 += s_misc[16 + wv * 2];
               pn2 += s_misc[16 + wv * 2 + 1];
             }
-            const float max_norm = P.alpha * sqrtf(pn2) / P.lr;      // :119
+            const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
             const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
             const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
 #pragma unroll
