@@ -35,8 +35,7 @@ constexpr int kGgsUnroll = 4;     // rounds (of 32 matches) per streaming chunk 
 constexpr int kRingStages = 4;    // chunks in flight per warp in the bulk-async ring (8 KB per warp, 128 KB per CTA)
 constexpr int kRingBytes = kGgsWarps * kRingStages * kGgsUnroll * 512 + kGgsWarps * kRingStages * 8;
 constexpr int kAccTail = 5;       // {g_fx', g_fy', clamp_sum, valid error sum (eval mode), valid count (int32 bits)}
-constexpr int kSegAcc = 12;       // per-segment sums: G[9], clamp_sum, valid error sum (eval mode), valid count (int32 bits)
-constexpr int kWarpSlots = 4;     // pair segments per chunk a warp can hand over through its own slots (beyond: shared atomics)
+constexpr int kSegAcc = 12;       // per-segment shared accumulators: G[9], clamp_sum, valid error sum, pad
 constexpr int kXchGroupDefault = 12;  // CTAs per exchange group (two-level all-reduce above this many CTAs per sequence)
 
 struct GgsProblem {
@@ -80,8 +79,7 @@ __host__ __device__ inline int ggs_xch_groups(int cpp, int group) { return group
 constexpr int kGgsFixedFloatsPerFrame = 2 * 9 + 4 * 9 + 4 + 18 + 14;  // pose, vel, R, A, Rt, At, fl, inr, gAt|gRt, partial + summed gradient
 
 __host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
-  size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 128 + (size_t)(2 * kGgsMaxSeg + kGgsWarps * kWarpSlots) * kSegAcc +
-                                  2 * kGgsWarps);
+  size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 128 + (size_t)kGgsMaxSeg * kSegAcc);
   bytes += kGgsMaxSeg * sizeof(int);         // segment valid counts
   bytes += 2 * (size_t)frames * sizeof(int);  // exchange plan: contributors per frame, own frames
   bytes += (kGgsMaxSeg + 1) * sizeof(int4);  // segment descriptors
@@ -250,12 +248,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   float* s_misc = s_fg + 2 * N9;    // [4] clamp_sum, [5] loss_sum, [8..11] sum over frames of d/d(ix, iy, kx, ky), [16..47] norm partials
   float* s_part = s_misc + 64;      // [N*7] this CTA's partial gradient of the iteration
   float* s_gsum = s_part + N * 7 + 32;  // [N*7 + kAccTail] summed gradient of this iteration (all CTAs: identical bits)
-  float* s_sacc = s_gsum + N * 7 + 32;  // [kGgsMaxSeg][kSegAcc] overflow accumulators (warps that visit > kWarpSlots segments)
-  float* s_gtot = s_sacc + kGgsMaxSeg * kSegAcc;              // [kGgsMaxSeg][kSegAcc] per-segment totals of the chunk
-  float* s_wacc = s_gtot + kGgsMaxSeg * kSegAcc;              // [kGgsWarps][kWarpSlots][kSegAcc] per-warp hand-over slots
-  int* s_wfirst = reinterpret_cast<int*>(s_wacc + kGgsWarps * kWarpSlots * kSegAcc);  // [kGgsWarps] first segment (chunk-local) of a warp
-  int* s_wn = s_wfirst + kGgsWarps;                           // [kGgsWarps] slots the warp filled in this chunk
-  int* s_scnt = s_wn + kGgsWarps;
+  float* s_sacc = s_gsum + N * 7 + 32;  // [kGgsMaxSeg][kSegAcc]
+  int* s_scnt = reinterpret_cast<int*>(s_sacc + kGgsMaxSeg * kSegAcc);
   int* s_expect = s_scnt + kGgsMaxSeg;  // [N] CTAs of this sequence that contribute to frame n (one-hop exchange)
   int* s_mine = s_expect + N;           // [N] 1 if this CTA's segments touch frame n
   float4* s_pts = reinterpret_cast<float4*>(smem_raw + ggs_smem_fixed_bytes(N));
@@ -298,7 +292,6 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   for (int e = tid; e < 2 * N9; e += kGgsThreads) s_fg[e] = 0.f;
   for (int e = tid; e < kGgsMaxSeg * kSegAcc; e += kGgsThreads) s_sacc[e] = 0.f;
   for (int e = tid; e < kGgsMaxSeg; e += kGgsThreads) s_scnt[e] = 0;
-  if (tid < kGgsWarps) { s_wfirst[tid] = 0; s_wn[tid] = 0; }
   if (tid < 64) s_misc[tid] = 0.f;
   if (tid == 0) s_cta_cnt = 0;
   if (single_chunk && cta_has_work && tid <= seg_hi - seg_lo + 1) s_seg[tid] = __ldg(&pr.segs[seg_lo + tid]);
@@ -416,24 +409,6 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         }
         // ---- stage 1: stream the matches of this warp's rounds ----
         {
-          // Hand-over of one (warp, segment) result: the warp's j-th segment of this chunk goes into its own slot j with plain
-          // stores (shared-memory float atomics are compare-and-swap loops on this hardware, ATOMS.CAST.SPIN: ~6 warps
-          // colliding on every segment cost more than the whole reduction); only a warp that walks more than kWarpSlots
-          // segments falls back to the atomic overflow accumulators.
-          int w_first = 0, w_used = 0;
-          auto hand_over = [&](int s_local, float tot, int slot, int nval) {
-            if (w_used == 0) w_first = s_local;
-            const int j = s_local - w_first;
-            if (j < kWarpSlots) {
-              float* dst = s_wacc + (warp * kWarpSlots + j) * kSegAcc;
-              if (!(lane & 1) && slot < 11) dst[slot] = tot;
-              if (lane == 0) dst[11] = __int_as_float(nval);
-              w_used = j + 1;
-            } else {
-              if (!(lane & 1) && slot < 11) atomicAdd(&s_sacc[s_local * kSegAcc + slot], tot);
-              if (lane == 0 && nval) atomicAdd(&s_scnt[s_local], nval);
-            }
-          };
           if (use_ring) {
             const int nr_w = r_w1 - r_w0;
             if (nr_w > 0) {
@@ -479,7 +454,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
                 nval = __reduce_add_sync(0xffffffffu, (int)g[11]);  // per-lane counts are exact small integers
                 const float tot = warp_reduce16(g, lane);
                 const int slot = warp_reduce16_slot(lane);
-                hand_over(s - cs, tot, slot, nval);
+                if (!(lane & 1) && slot < 11) atomicAdd(&s_sacc[(s - cs) * kSegAcc + slot], tot);
+                if (lane == 0 && nval) atomicAdd(&s_scnt[s - cs], nval);
               };
               begin_segment();
               for (int c = 0; c < nch; ++c) {
@@ -671,75 +647,43 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             nval = __reduce_add_sync(0xffffffffu, (int)g[11]);  // per-lane counts are exact small integers
             const float tot = warp_reduce16(g, lane);
             const int slot = warp_reduce16_slot(lane);
-            hand_over(s - cs, tot, slot, nval);
+            if (!(lane & 1) && slot < 11) atomicAdd(&s_sacc[(s - cs) * kSegAcc + slot], tot);
+            if (lane == 0 && nval) atomicAdd(&s_scnt[s - cs], nval);
             r = r_end;
             ++s;
           }
           }
-          if (lane == 0) {
-            s_wfirst[warp] = w_first;
-            s_wn[warp] = w_used;
-          }
         }
         __syncthreads();
         if (pr.dbg_clock && tid == 0) ck1a = clock64();
-        // ---- stage 2a (i): per-segment totals = the warps' slots (fixed warp order) + the overflow accumulators ----
-        for (int t = tid; t < nchunk * kSegAcc; t += kGgsThreads) {
-          const int sl = t / kSegAcc, k = t - sl * kSegAcc;
-          float tot = s_sacc[t];
-          int cnt = (k == 11) ? s_scnt[sl] : 0;
-          s_sacc[t] = 0.f;  // the overflow accumulators are left zeroed
-          if (k == 11) s_scnt[sl] = 0;
-#pragma unroll 4
-          for (int wv = 0; wv < kGgsWarps; ++wv) {
-            const int j = sl - s_wfirst[wv];
-            if (j >= 0 && j < s_wn[wv]) {
-              const float v = s_wacc[(wv * kWarpSlots + j) * kSegAcc + k];
-              if (k == 11) cnt += __float_as_int(v);
-              else tot += v;
-            }
+        // ---- stage 2a: per-pair adjoint, one warp per segment, 18 lanes x 2 outputs; leaves the slots zeroed ----
+        for (int sl = warp; sl < nchunk; sl += kGgsWarps) {
+          const int4 sd = s_seg[sl];
+          float* G = s_sacc + sl * kSegAcc;
+          float g3[3] = {0.f, 0.f, 0.f}, gs = 0.f;
+          const int side = lane >= 9, e = (lane - side * 9) % 9, i = e / 3, j = e - i * 3;
+          if (lane < 18) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g3[k] = side ? G[k * 3 + i] : G[i * 3 + k];
+            if (kEval && pr.dbg_G && lane < 9) atomicAdd(&pr.dbg_G[(size_t)(cs + sl) * 9 + lane], G[lane]);
+          } else if (lane < 20) {
+            gs = G[9 + (lane - 18)];
           }
-          s_gtot[t] = (k == 11) ? __int_as_float(cnt) : tot;
-          if (kEval && pr.dbg_G && k < 9) atomicAdd(&pr.dbg_G[(size_t)(cs + sl) * 9 + k], tot);
-        }
-        __syncthreads();
-        // ---- stage 2a (ii): per-pair adjoint as a gather: thread (frame n, slot) sums the contributions of the chunk's segments
-        // that involve n (slot < 9: gAt entry (i, j), else gRt entry (i, j)):  gAt_a -= G Rt_b,  gRt_a -= G At_b,
-        // gAt_b -= G^T Rt_a,  gRt_b -= G^T At_a.  Every entry has one owner: plain stores, fixed summation order.
-        for (int task = tid; task < N * 18; task += kGgsThreads) {
-          const int n = task / 18, sl18 = task - n * 18;
-          const int which = sl18 >= 9, e = sl18 - which * 9, i = e / 3, j = e - i * 3;
-          float acc = (cs == seg_lo) ? 0.f : s_fg[task];
-          const float* oth_base = which ? s_At : s_Rt;
-          for (int sl = 0; sl < nchunk; ++sl) {
-            const int4 sd = s_seg[sl];
-            const float* G = s_gtot + sl * kSegAcc;
-            if (sd.z == n) {  // n is the first frame of the pair: row i of G, the other frame's terms
-              const float* o = oth_base + sd.w * 9;
-              acc -= G[i * 3 + 0] * o[0 + j] + G[i * 3 + 1] * o[3 + j] + G[i * 3 + 2] * o[6 + j];
-            }
-            if (sd.w == n) {  // n is the second frame: column i of G
-              const float* o = oth_base + sd.z * 9;
-              acc -= G[0 + i] * o[0 + j] + G[3 + i] * o[3 + j] + G[6 + i] * o[6 + j];
-            }
-          }
-          s_fg[task] = acc;
-        }
-        if (warp == kGgsWarps - 1) {  // CTA-level scalars: clamped error sum, valid error sum (eval mode), valid count
-          float cs_sum = 0.f, ls_sum = 0.f;
-          int cnt = 0;
-          for (int sl = lane; sl < nchunk; sl += 32) {
-            cs_sum += s_gtot[sl * kSegAcc + 9];
-            ls_sum += s_gtot[sl * kSegAcc + 10];
-            cnt += __float_as_int(s_gtot[sl * kSegAcc + 11]);
-          }
-          cs_sum = warp_sum(cs_sum);
-          ls_sum = warp_sum(ls_sum);
-          cnt = __reduce_add_sync(0xffffffffu, cnt);
-          if (lane == 0) {
-            s_misc[4] += cs_sum;
-            s_misc[5] += ls_sum;
-            s_cta_cnt += cnt;
+          const int cnt_seg = s_scnt[sl];
+          __syncwarp();
+          if (lane < kSegAcc) G[lane] = 0.f;
+          if (lane == 0) s_scnt[sl] = 0;
+          if (lane < 18) {
+            const int self = side ? sd.w : sd.z, other = side ? sd.z : sd.w;
+            float oA, oR;
+            pair_adjoint_entry(g3, s_At + other * 9, s_Rt + other * 9, j, &oA, &oR);
+            atomicAdd(&s_fg[self * 18 + e], oA);
+            atomicAdd(&s_fg[self * 18 + 9 + e], oR);
+          } else if (lane == 18) {
+            atomicAdd(&s_misc[4], gs);
+            atomicAdd(&s_cta_cnt, cnt_seg);
+          } else if (lane == 19 && kEval) {
+            atomicAdd(&s_misc[5], gs);
           }
         }
       }
@@ -759,6 +703,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             float gA[9], gR[9];
             frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
             frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
+#pragma unroll
+            for (int k = 0; k < 18; ++k) gAt[k] = 0.f;
           }
 #pragma unroll
           for (int k = 0; k < 3; ++k) s_part[n * 7 + k] = gT[k];
