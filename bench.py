@@ -327,8 +327,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU GGS iterations in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ggs-layout", default="plain", choices=["plain", "paired"],
-                    help="HBM layout of the packed match stream (csrc/ggs_layout.cuh); 'paired' is experimental, see DESIGN.md 4.1")
+    ap.add_argument("--ggs-layout", default="paired", choices=["plain", "paired"],
+                    help="HBM layout of the packed match stream (csrc/ggs_layout.cuh); 'paired' is the library default, see DESIGN.md 4.1")
     ap.add_argument("--denoiser-engine", default="auto", choices=["auto", "fp32", "tf32"],
                     help="auto = exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tiles (TF32) at or above")
     args = ap.parse_args()

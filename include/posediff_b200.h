@@ -151,10 +151,10 @@ void pdb_matches_free(pdb_matches* m);
 int pdb_matches_info(const pdb_matches* m, int64_t* m_total, int32_t* segments, int64_t* rounds, int32_t* frames);
 
 /* Layout of the packed match stream in HBM for match sets packed on this context from now on (csrc/ggs_layout.cuh):
- * 0 = plain (one float4 per match, segments padded to 32-row rounds; the default and the layout every round-1 number
- * was measured with), 1 = paired (segments padded to 64-row units, the two matches of a lane component-interleaved so
- * that the 128-bit loads are directly the operand pairs of the packed fp32x2 pipe).  Same 16 B per match, same results;
- * the environment variable PDB_GGS_LAYOUT=paired selects 1 at pdb_create.  EXPERIMENTAL until measured on a B200. */
+ * 1 = paired (the default: segments padded to 64-row units, the two matches of a lane component-interleaved so that the
+ * 128-bit loads are directly the operand pairs of the packed fp32x2 pipe), 0 = plain (one float4 per match, segments padded
+ * to 32-row rounds; the layout the round-1 numbers were measured with).  Same 16 B per match, same results (tests/
+ * test_gpu_layout.py); the environment variable PDB_GGS_LAYOUT=plain|paired overrides the default at pdb_create. */
 int pdb_ggs_layout(pdb_context* ctx, int32_t layout);
 int pdb_ggs_layout_get(const pdb_context* ctx); /* the layout new match sets are packed in (0 / 1) */
 

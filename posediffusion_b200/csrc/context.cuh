@@ -45,7 +45,7 @@ struct Context {
   void* vit_ws = nullptr;
   size_t vit_ws_bytes = 0;
   size_t attr_vit_att[4] = {0, 0, 0, 0};
-  int ggs_layout = 0;       // stream layout of match sets packed on this context (ggs_layout.cuh): 0 plain, 1 paired
+  int ggs_layout = 1;       // stream layout of match sets packed on this context (ggs_layout.cuh): 0 plain, 1 paired (default)
   int denoiser_engine = 0;  // 0 auto, 1 fp32 persistent kernel, 2 tcgen05/TMA tiles (TF32)
   // optional per-kernel timing (bench.py roofline): event pairs per launch, kind 0 = GGS, 1 = denoiser
   bool profiling = false;

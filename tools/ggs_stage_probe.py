@@ -6,7 +6,7 @@ from posediffusion_b200 import synthetic as syn, _native
 frames, per_pair = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (20, 2048)
 dev = torch.device('cuda:0')
 ctx = _native.Context.get(dev)
-ctx.set_ggs_layout(sys.argv[3] if len(sys.argv) > 3 else 'plain')  # plain | paired (csrc/ggs_layout.cuh)
+ctx.set_ggs_layout(sys.argv[3] if len(sys.argv) > 3 else 'paired')  # plain | paired (csrc/ggs_layout.cuh)
 m = syn.uniform_matches(frames, per_pair, seed=0)
 pm = ctx.pack_matches(m)
 _, _, start = syn.scene_matches(frames, 4, seed=1)
