@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "context.cuh"
 #include "tc_linear.cuh"
@@ -65,10 +66,41 @@ static int launch_tc_linear(Context* ctx, const float* X, const float* W, const 
   return PDB_OK;
 }
 
+// Swap-AB launch (few tokens): weights on the 128-row M side, NT tokens on the N side (tc_linear.cuh header).
+template <int NT>
+static int launch_tc_linear_swap(Context* ctx, const float* X, const float* W, const TcEpilogue& E, bool& attr, cudaStream_t st) {
+  CUtensorMap mx, mw;
+  if (int rc = make_map(ctx, &mx, X, E.S, E.K, NT)) return rc;
+  if (int rc = make_map(ctx, &mw, W, E.O, E.K, kTcBM)) return rc;
+  const size_t smem = tc_smem_bytes(NT, kTcStages);
+  if (!attr) {
+    PDB_CUDA(ctx, (cudaFuncSetAttribute(tc_linear_kernel<NT, kTcStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    attr = true;
+  }
+  const int tiles = (E.O / kTcBM) * ((E.S + NT - 1) / NT);
+  const int grid = std::min(tiles, 2 * ctx->sm_count);
+  {
+    ScopedTimer timer(ctx, st, 1);
+    tc_linear_kernel<NT, kTcStages, true><<<grid, kTcThreads, smem, st>>>(mx, mw, E);
+  }
+  PDB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return PDB_OK;
+}
+
 // Y = epilogue(X[S,K] @ W[O,K]^T) on the tensor cores.  K % 32 == 0, O % 64 == 0, all pointers 16-byte aligned.
-// 128-feature tiles (UMMA 128x128x8) when they still fill the machine, 64-feature tiles for the small-S denoiser shapes.
+// 128-feature tiles (UMMA 128x128x8) when they still fill the machine, 64-feature tiles for the small-S denoiser shapes,
+// swap-AB tiles (weights on the M side) when there are at most 96 tokens (PDB_TC_SWAP=0 disables them for A/B timing).
 int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st) {
   if (E.K % kTcBK || E.O % 64 || E.S < 1) return ctx->fail(PDB_ERR_INVALID, "tc_linear shape (S=%d, O=%d, K=%d)", E.S, E.O, E.K);
+  if (E.S <= 96 && E.O % kTcBM == 0) {
+    static const bool swap_on = [] { const char* v = getenv("PDB_TC_SWAP"); return !(v && v[0] == '0'); }();
+    if (swap_on) {
+      if (E.S <= 32) return launch_tc_linear_swap<32>(ctx, X, W, E, ctx->attr_tc_swap[0], st);
+      if (E.S <= 64) return launch_tc_linear_swap<64>(ctx, X, W, E, ctx->attr_tc_swap[1], st);
+      return launch_tc_linear_swap<96>(ctx, X, W, E, ctx->attr_tc_swap[2], st);
+    }
+  }
   E.vec8 = (reinterpret_cast<uintptr_t>(E.Y) % 32 == 0) && (E.ldy % 8 == 0) &&
            (!E.residual || (reinterpret_cast<uintptr_t>(E.residual) % 32 == 0 && E.ldr % 8 == 0));
   const long long wide_tiles = (long long)(E.O / 128) * ((E.S + kTcBM - 1) / kTcBM);

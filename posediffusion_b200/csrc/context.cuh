@@ -40,6 +40,7 @@ struct Context {
   // cudaFuncSetAttribute is per device: remember per context (= per device) what was already requested
   size_t attr_ggs[4] = {0, 0, 0, 0}, attr_den[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
   bool attr_tc = false, attr_tc128 = false;
+  bool attr_tc_swap[3] = {false, false, false};  // swap-AB instantiations (32 / 64 / 96 tokens on the N side)
   // image feature extractor (csrc/api_vit.cu)
   VitWeights* vit = nullptr;
   void* vit_ws = nullptr;

@@ -9,6 +9,11 @@
 //   * `tcgen05.commit` releases ring slots / signals the epilogue; 4 epilogue warps read TMEM with `tcgen05.ld`
 //     (32 lanes x 32 columns per instruction) and apply bias / folded LayerNorm / residual / ReLU on the way to HBM.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (one TMEM lane quarter each).
+//
+// Swap-AB instantiation (kSwap, few tokens: S <= 96): the WEIGHTS take the 128-row UMMA M side (A = 128 features x 32 k) and
+// the tokens the N side (B = BN tokens x 32 k, BN = 32 / 64 / 96, rows beyond S zero-filled by TMA), i.e. the tile computes
+// Y^T[128 features, BN tokens].  No tensor-core work is spent on padding tokens up to 128 rows; an accumulator row (TMEM
+// lane) is a feature, so an epilogue warp stores 32 consecutive features of one token per instruction (128 contiguous bytes).
 #pragma once
 #include <cuda.h>
 
@@ -104,10 +109,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent: every CTA walks the tile list (tile = blockIdx.x, + gridDim.x, ...; feature-tile index fastest so that CTAs running
 // side by side share the same 128 token rows in L2).  The accumulator is double buffered in TMEM (2 x BN columns): while the four
 // epilogue warps drain tile i, the TMA and MMA warps are already inside tile i+1.
-template <int BN, int ST = kTcStages>
+template <int BN, int ST = kTcStages, bool kSwap = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcEpilogue E) {
-  static_assert(BN == 64 || BN == 128, "feature tile");
+  static_assert(kSwap ? (BN == 32 || BN == 64 || BN == 96) : (BN == 64 || BN == 128), "N-side tile");
+  constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : 256;  // two accumulators, power of two >= 32
   extern __shared__ unsigned char tc_smem_raw[];
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -123,8 +129,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = E.K / kTcBK;
-  const int n_tiles = E.O / BN;
-  const int total_tiles = n_tiles * ((E.S + kTcBM - 1) / kTcBM);
+  // tile list: the N-side index runs fastest.  normal: M side = 128 tokens, N side = BN features; swap: M side = 128 features,
+  // N side = BN tokens.  (m0, n0) below are always (M-side offset, N-side offset).
+  const int n_tiles = kSwap ? (E.S + BN - 1) / BN : E.O / BN;
+  const int total_tiles = n_tiles * (kSwap ? E.O / kTcBM : (E.S + kTcBM - 1) / kTcBM);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -140,7 +148,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 1) {  // TMEM allocation: two BN-column fp32 accumulators (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -158,8 +166,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const uint32_t ph = (it / ST) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
           mbar_arrive_expect_tx(full_bar(s), kStageBytes);
-          tma_load_2d(base + s * kStageBytes, &map_x, kb * kTcBK, m0, full_bar(s));
-          tma_load_2d(base + s * kStageBytes + kABytes, &map_w, kb * kTcBK, n0, full_bar(s));
+          tma_load_2d(base + s * kStageBytes, kSwap ? &map_w : &map_x, kb * kTcBK, m0, full_bar(s));
+          tma_load_2d(base + s * kStageBytes + kABytes, kSwap ? &map_x : &map_w, kb * kTcBK, n0, full_bar(s));
         }
       }
     }
@@ -197,6 +205,35 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int buf = lt & 1;
       mbar_wait(tmem_full_bar(buf), (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if constexpr (kSwap) {
+        // accumulator row (TMEM lane) = feature o, column = token: one warp store covers 32 consecutive features of a token
+        const int o = m0 + quarter * 32 + lane;
+        const float b_o = bias ? __ldg(bias + o) : 0.f;
+        const float cs_o = E.colsum ? __ldg(E.colsum + o) : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+          if (c0 + 32 == BN) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty_bar(buf));
+          }
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const int srow = n0 + c0 + t;
+            if (srow < E.S) {  // warp-uniform
+              float x = v[t];
+              if (E.colsum) x = __ldg(E.row_rstd + srow) * (x - __ldg(E.row_mean + srow) * cs_o);
+              x += b_o;
+              if (E.residual) x += E.residual[(size_t)srow * E.ldr + o];
+              if (E.relu) x = fmaxf(x, 0.f);
+              if (E.gelu) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+              E.Y[(size_t)srow * E.ldy + o] = x;
+            }
+          }
+        }
+        continue;
+      }
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < E.S;
       float mean = 0.f, rstd = 1.f;
@@ -262,7 +299,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols) : "memory");
   }
 }
 
