@@ -387,7 +387,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   __syncthreads();
   frames_forward();
 
-  __shared__ long long clk_sum[8];  // probe (thread 0): {-, stage 1, stage 2b, exchange, stage 2a, iterations, stage 3 + 0, -}
+  __shared__ long long clk_sum[8];  // probe (thread 0): {stage 3 norms, stage 1, stage 2b, exchange, stage 2a, iterations, next stage 0, stage 3 update}
   if (tid < 8) clk_sum[tid] = 0;
   for (int phase = 0; phase < P.n_phases; ++phase) {
     const int flags = P.flags[phase];
@@ -798,6 +798,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               }
             }
             __syncthreads();
+            if (pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: norm partials
             gn2 = 0.f;
             pn2 = 0.f;
             for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
@@ -822,6 +823,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             }
             ++done;
             __syncthreads();
+            if (pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[7] += c - ck3; ck3 = c; }  // probe: coefficient + update
             frames_forward();  // stage 0 of the next iteration (one block barrier inside)
           }
         }
