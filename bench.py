@@ -499,7 +499,7 @@ def main():
         algo_bytes = ALGO_BYTES_PER_MATCH_EVAL * m_total * inner_per_launch * B
         achieved = algo_bytes / (ggs_ms / ggs_n / 1000.0) / 1e9
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
             rec = json.load(open(tpath)).get(f"ggs_entry<false>@{args.workload}")
             if rec and B == 1:
