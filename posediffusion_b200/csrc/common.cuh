@@ -119,6 +119,8 @@ inline void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 inline void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) { emu::bulk_copy_g2s(dst_smem, src, bytes, bar); }
+inline uint64_t l2_policy_evict_first() { return 0; }
+inline void bulk_copy_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t) { emu::bulk_copy_g2s(dst_smem, src, bytes, bar); }
 #else
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;
@@ -193,6 +195,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// The same with an L2 eviction policy: the match stream of a big sequence (414 MB per inner iteration at config 5) passes
+// through L2 exactly once per iteration and would otherwise evict the few hot lines every CTA polls and adds to (the exchange
+// accumulators: 3.2 GB of DRAM write-backs per launch and DRAM-latency polls without the hint).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_copy_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {

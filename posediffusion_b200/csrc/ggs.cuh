@@ -417,8 +417,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
                 const int st = c % kRingStages;
                 const int rounds_c = min(kGgsUnroll, nr_w - c * kGgsUnroll);
                 mbar_arrive_expect_tx(ring_bar + st * 8, rounds_c * 512);
-                bulk_copy_g2s(ring_base + st * (kGgsUnroll * 512), pr.pts + (size_t)(r_w0 + c * kGgsUnroll) * 32, rounds_c * 512,
-                              ring_bar + st * 8);
+                bulk_copy_g2s_hint(ring_base + st * (kGgsUnroll * 512), pr.pts + (size_t)(r_w0 + c * kGgsUnroll) * 32, rounds_c * 512,
+                                   ring_bar + st * 8, l2_policy_evict_first());  // the stream must not evict the exchange accumulators from L2
               };
               if (lane == 0)
                 for (int c = 0; c < min(kRingStages, nch); ++c) issue(c);
