@@ -656,38 +656,51 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         }
         __syncthreads();
         if (pr.dbg_clock && tid == 0) ck1a = clock64();
-        // ---- stage 2a: per-pair adjoint, one warp per segment, 18 lanes x 2 outputs; leaves the slots zeroed ----
-        for (int sl = warp; sl < nchunk; sl += kGgsWarps) {
-          const int4 sd = s_seg[sl];
-          float* G = s_sacc + sl * kSegAcc;
-          float g3[3] = {0.f, 0.f, 0.f}, gs = 0.f;
+        // ---- stage 2a: per-pair adjoint.  ONE warp walks the chunk's segments one after the other, 18 lanes x 2 outputs each, and
+        // adds into the per-frame slots with plain read-modify-writes (side a, then side b: a diagonal pair hits the same slots
+        // twice).  Shared-memory float atomics are compare-and-swap loops on this hardware (ATOMS.CAST.SPIN) and the segments of
+        // a CTA share frames, so one warp per segment with atomics was slower (1.4 k cycles for 3 segments; 5 k for 43). ----
+        if (warp == 0) {
           const int side = lane >= 9, e = (lane - side * 9) % 9, i = e / 3, j = e - i * 3;
-          if (lane < 18) {
+          float gs_sum = 0.f;  // lane 18: clamped error sum, lane 19: valid error sum (eval mode)
+          int cnt_sum = 0;     // lane 20: valid count
+          for (int sl = 0; sl < nchunk; ++sl) {
+            const int4 sd = s_seg[sl];
+            float* G = s_sacc + sl * kSegAcc;
+            float g3[3] = {0.f, 0.f, 0.f};
+            if (lane < 18) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) g3[k] = side ? G[k * 3 + i] : G[i * 3 + k];
-            if (kEval && pr.dbg_G && lane < 9) atomicAdd(&pr.dbg_G[(size_t)(cs + sl) * 9 + lane], G[lane]);
-          } else if (lane < 20) {
-            gs = G[9 + (lane - 18)];
-          }
-          const int cnt_seg = s_scnt[sl];
-          __syncwarp();
-          if (lane < kSegAcc) G[lane] = 0.f;
-          if (lane == 0) s_scnt[sl] = 0;
-          if (lane < 18) {
+              for (int k = 0; k < 3; ++k) g3[k] = side ? G[k * 3 + i] : G[i * 3 + k];
+              if (kEval && pr.dbg_G && lane < 9) atomicAdd(&pr.dbg_G[(size_t)(cs + sl) * 9 + lane], G[lane]);
+            } else if (lane < 20) {
+              gs_sum += G[9 + (lane - 18)];
+            } else if (lane == 20) {
+              cnt_sum += s_scnt[sl];
+            }
+            __syncwarp();
+            if (lane < kSegAcc) G[lane] = 0.f;  // the segment accumulators are left zeroed for the next iteration
+            if (lane == 0) s_scnt[sl] = 0;
+            float oA = 0.f, oR = 0.f;
             const int self = side ? sd.w : sd.z, other = side ? sd.z : sd.w;
-            float oA, oR;
-            pair_adjoint_entry(g3, s_At + other * 9, s_Rt + other * 9, j, &oA, &oR);
-            atomicAdd(&s_fg[self * 18 + e], oA);
-            atomicAdd(&s_fg[self * 18 + 9 + e], oR);
-          } else if (lane == 18) {
-            atomicAdd(&s_misc[4], gs);
-            atomicAdd(&s_cta_cnt, cnt_seg);
-          } else if (lane == 19 && kEval) {
-            atomicAdd(&s_misc[5], gs);
+            if (lane < 18) pair_adjoint_entry(g3, s_At + other * 9, s_Rt + other * 9, j, &oA, &oR);
+            if (lane < 9) {
+              s_fg[self * 18 + e] += oA;
+              s_fg[self * 18 + 9 + e] += oR;
+            }
+            __syncwarp();
+            if (lane >= 9 && lane < 18) {
+              s_fg[self * 18 + e] += oA;
+              s_fg[self * 18 + 9 + e] += oR;
+            }
+            __syncwarp();
           }
+          if (lane == 18) s_misc[4] += gs_sum;
+          if (lane == 19 && kEval) s_misc[5] += gs_sum;
+          if (lane == 20) s_cta_cnt += cnt_sum;
         }
       }
-      __syncthreads();
+      if (N > 32) __syncthreads();  // frames beyond the first warp: their threads wait for warp 0's stage 2a
+      else __syncwarp();
       if (pr.dbg_clock && tid == 0) ck1 = clock64();
       // ================= stage 2b: one thread per frame: unfold K, frame adjoint -> the CTA's partial gradient =================
       if (warp * 32 < N) {  // the warps that hold frames (one thread per frame)
