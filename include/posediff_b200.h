@@ -94,6 +94,10 @@ int pdb_profile_read(pdb_context* ctx, double* ggs_ms, int64_t* ggs_launches, do
  * enable = 0 frees the buffer. */
 int pdb_debug_ggs_clocks(pdb_context* ctx, int32_t enable, int64_t* out, int32_t max_ctas);
 
+/* Swap-AB tcgen05 tiles (weights on the 128-row UMMA M side, 32 / 64 / 96 tokens on the N side) for GEMMs with at most 96 tokens
+ * and O % 128 == 0; default off (measured slower than 128-token tiles without split-K).  Debug / measurement switch. */
+int pdb_debug_tc_swap(pdb_context* ctx, int32_t on);
+
 /* Denoiser engine: 0 = auto (exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tensor-core tiles with TF32
  * products at or above), 1 = always fp32, 2 = always tensor cores. */
 int pdb_denoiser_engine(pdb_context* ctx, int32_t mode);

@@ -78,6 +78,7 @@ EXPORTS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "pdb_matches_free": (None, [C.c_void_p]),
     "pdb_matches_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "pdb_debug_tc_swap": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_ggs_layout": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_ggs_layout_get": (C.c_int, [C.c_void_p]),
     "pdb_debug_pack_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
@@ -267,6 +268,10 @@ class Context:
     def set_denoiser_engine(self, mode: str = "auto"):
         """'auto' (fp32 kernel below 128 tokens, tensor cores above), 'fp32' or 'tf32'."""
         self._ok(self.lib.pdb_denoiser_engine(self.handle, {"auto": 0, "fp32": 1, "tf32": 2}[mode]), "pdb_denoiser_engine")
+
+    def set_tc_swap(self, on: bool):
+        """Swap-AB tcgen05 tiles for GEMMs with at most 96 tokens (default off; see profiles/r2_bench_tc_small.json)."""
+        self._ok(self.lib.pdb_debug_tc_swap(self.handle, int(on)), "pdb_debug_tc_swap")
 
     def set_ggs_layout(self, layout: str = "plain"):
         """Stream layout of match sets packed from now on: 'plain' (default) or 'paired' (csrc/ggs_layout.cuh; experimental)."""

@@ -90,12 +90,14 @@ static int launch_tc_linear_swap(Context* ctx, const float* X, const float* W, c
 
 // Y = epilogue(X[S,K] @ W[O,K]^T) on the tensor cores.  K % 32 == 0, O % 64 == 0, all pointers 16-byte aligned.
 // 128-feature tiles (UMMA 128x128x8) when they still fill the machine, 64-feature tiles for the small-S denoiser shapes,
-// swap-AB tiles (weights on the M side) when there are at most 96 tokens (PDB_TC_SWAP=0 disables them for A/B timing).
+// swap-AB tiles (weights on the M side) for at most 96 tokens when enabled (pdb_debug_tc_swap / PDB_TC_SWAP=1).
 int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st) {
   if (E.K % kTcBK || E.O % 64 || E.S < 1) return ctx->fail(PDB_ERR_INVALID, "tc_linear shape (S=%d, O=%d, K=%d)", E.S, E.O, E.K);
   if (E.S <= 96 && E.O % kTcBM == 0) {
-    static const bool swap_on = [] { const char* v = getenv("PDB_TC_SWAP"); return !(v && v[0] == '0'); }();
-    if (swap_on) {
+    // default off: without split-K only O/128 CTAs stream the weights and the tile is bound by one SM's L2 bandwidth
+    // (profiles/r2_bench_tc_small.json: slower than padding the tokens to a 128-row tile except at 5 tokens)
+    static const bool env_on = [] { const char* v = getenv("PDB_TC_SWAP"); return v && v[0] == '1'; }();
+    if (env_on || ctx->tc_swap) {
       if (E.S <= 32) return launch_tc_linear_swap<32>(ctx, X, W, E, ctx->attr_tc_swap[0], st);
       if (E.S <= 64) return launch_tc_linear_swap<64>(ctx, X, W, E, ctx->attr_tc_swap[1], st);
       return launch_tc_linear_swap<96>(ctx, X, W, E, ctx->attr_tc_swap[2], st);
@@ -306,6 +308,12 @@ int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
 }
 
 }  // namespace pdb
+
+extern "C" int pdb_debug_tc_swap(pdb_context* c, int32_t on) {
+  if (!c) return PDB_ERR_INVALID;
+  reinterpret_cast<Context*>(c)->tc_swap = on != 0;
+  return PDB_OK;
+}
 
 extern "C" int pdb_denoiser_engine(pdb_context* c, int32_t mode) {
   if (!c || mode < 0 || mode > 2) return PDB_ERR_INVALID;

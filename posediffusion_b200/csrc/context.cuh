@@ -40,6 +40,7 @@ struct Context {
   // cudaFuncSetAttribute is per device: remember per context (= per device) what was already requested
   size_t attr_ggs[4] = {0, 0, 0, 0}, attr_den[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
   bool attr_tc = false, attr_tc128 = false;
+  bool tc_swap = false;     // swap-AB tcgen05 tiles for <= 96 tokens (pdb_debug_tc_swap); default off, see profiles/r2_bench_tc_small.json
   bool attr_tc_swap[3] = {false, false, false};  // swap-AB instantiations (32 / 64 / 96 tokens on the N side)
   // image feature extractor (csrc/api_vit.cu)
   VitWeights* vit = nullptr;

@@ -1,6 +1,6 @@
 """Tensor-core engine below 128 tokens (swap-AB tiles) against the exact-fp32 persistent kernel: time per diffusion step.
 
-    python tools/tc_small_probe.py            # prints one JSON line; run once with PDB_TC_SWAP=0 for the 128-token-tile kernel
+    python tools/tc_small_probe.py            # prints one JSON line; run once more with PDB_TC_SWAP=1 for the swap-AB tiles
 """
 import json, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +12,7 @@ den = pdb.Denoiser(TRANSFORMER=dict(d_model=512, nhead=4, dim_feedforward=1024, 
 den.load_state_dict(syn.random_denoiser_state(0), strict=True)
 den = den.to(dev)
 ctx = den.native_context()
-out = {"tc_swap": os.environ.get("PDB_TC_SWAP", "1")}
+out = {"tc_swap": os.environ.get("PDB_TC_SWAP", "0")}
 for batch, frames in ((1, 5), (1, 20), (1, 80), (4, 20)):
     z = syn.random_features(batch, frames, 0).to(dev)
     draws = syn.predraw_noise(batch, frames, seed=0).to(dev)
