@@ -137,17 +137,10 @@ __device__ __forceinline__ void sampson_match2_unit(const float4 X, const float4
 // 16-loads-in-flight polling loops would otherwise compete for registers with the streaming loop of stage 1.
 template <bool kEval>
 __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned long long* xch2, float* accbase, int cpp, int cta, int group,
-                                          int N, unsigned it_global, const float* s_part, const float* s_misc, int cta_cnt, float cx,
-                                          float cy, float* s_gsum, const int* s_expect, const int* s_mine) {
+                                          int N, unsigned it_global, const float* s_part, const float* s_misc, int cta_cnt, float g_fx,
+                                          float g_fy, float* s_gsum, const int* s_expect, const int* s_mine) {
   const int tid = threadIdx.x;
   const int nsum = ggs_xch_words(N);
-  if (tid >= (nsum + 31) / 32 * 32) return;  // warps without an element go straight to the block barrier (issue slots are shared)
-  // adjoint of the shared focal lengths from the summed intrinsics' adjoint (s_misc[8..11]) and f' = s_misc[12..13]
-  float g_fx = 0.f, g_fy = 0.f;
-  if (tid == N * 7 % kGgsThreads || tid == (N * 7 + 1) % kGgsThreads) {
-    g_fx = (-s_misc[8] + cx * s_misc[10]) / (s_misc[12] * s_misc[12]);
-    g_fy = (-s_misc[9] + cy * s_misc[11]) / (s_misc[13] * s_misc[13]);
-  }
   if (accbase) {
     // ONE hop: a CTA adds {value, 1} to the accumulators of the frames its segments touch (s_mine; zeros if the gradient of a
     // touched frame happens to vanish) and to the five scalars; an accumulator of frame n expects s_expect[n] arrivals, a scalar
@@ -348,49 +341,43 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
     *inr = (ev >= kFlMin && ev <= kFlMax) ? 1.f : 0.f;
   };
   auto frames_forward = [&]() {
-    if (warp * 32 < 4 * N) {  // the warps that hold (frame, column) threads; the others go straight to the barrier
-      {  // shared focal length = mean over frames (geometry_guided_sampling.py:142), reduced redundantly per warp
-        float fx = 0.f, fy = 0.f;
-        for (int m = lane; m < N; m += 32) {
-          fx += s_fl[m * 2];
-          fy += s_fl[m * 2 + 1];
-        }
-        fpx = warp_sum(fx) * scale_over_N;
-        fpy = warp_sum(fy) * scale_over_N;
-        kin[0] = 1.f / fpx;
-        kin[1] = 1.f / fpy;
-        kin[2] = -cx * kin[0];
-        kin[3] = -cy * kin[1];
-        if (tid == 0) {
-          s_misc[12] = fpx;
-          s_misc[13] = fpy;
-        }
+    {  // shared focal length = mean over frames (geometry_guided_sampling.py:142), reduced redundantly per warp
+      float fx = 0.f, fy = 0.f;
+      for (int m = lane; m < N; m += 32) {
+        fx += s_fl[m * 2];
+        fy += s_fl[m * 2 + 1];
       }
-      const int n = tid >> 2, j = tid & 3;
-      if (n < N && j < 3) {
-        const float* p = s_pose + n * 9;
-        const float w = p[3], x = p[4], y = p[5], z = p[6];
-        const float s2 = 2.0f / (w * w + x * x + y * y + z * z);
-        // row j of the pytorch3d rotation = column j of R_cv up to the signs D = diag(-1,-1,1) on the rows
-        float r0, r1, r2;
-        if (j == 0) { r0 = 1.f - s2 * (y * y + z * z); r1 = s2 * (x * y - z * w); r2 = s2 * (x * z + y * w); }
-        else if (j == 1) { r0 = s2 * (x * y + z * w); r1 = 1.f - s2 * (x * x + z * z); r2 = s2 * (y * z - x * w); }
-        else { r0 = s2 * (x * z - y * w); r1 = s2 * (y * z + x * w); r2 = 1.f - s2 * (x * x + y * y); }
-        const float Rc[3] = {-r0, -r1, r2};
-        const float tx = -p[0], ty = -p[1], tz = p[2];
-        const float Ac[3] = {-tz * Rc[1] + ty * Rc[2], tz * Rc[0] - tx * Rc[2], -ty * Rc[0] + tx * Rc[1]};
+      fpx = warp_sum(fx) * scale_over_N;
+      fpy = warp_sum(fy) * scale_over_N;
+      kin[0] = 1.f / fpx;
+      kin[1] = 1.f / fpy;
+      kin[2] = -cx * kin[0];
+      kin[3] = -cy * kin[1];
+    }
+    const int n = tid >> 2, j = tid & 3;
+    if (n < N && j < 3) {
+      const float* p = s_pose + n * 9;
+      const float w = p[3], x = p[4], y = p[5], z = p[6];
+      const float s2 = 2.0f / (w * w + x * x + y * y + z * z);
+      // row j of the pytorch3d rotation = column j of R_cv up to the signs D = diag(-1,-1,1) on the rows
+      float r0, r1, r2;
+      if (j == 0) { r0 = 1.f - s2 * (y * y + z * z); r1 = s2 * (x * y - z * w); r2 = s2 * (x * z + y * w); }
+      else if (j == 1) { r0 = s2 * (x * y + z * w); r1 = 1.f - s2 * (x * x + z * z); r2 = s2 * (y * z - x * w); }
+      else { r0 = s2 * (x * z - y * w); r1 = s2 * (y * z + x * w); r2 = 1.f - s2 * (x * x + y * y); }
+      const float Rc[3] = {-r0, -r1, r2};
+      const float tx = -p[0], ty = -p[1], tz = p[2];
+      const float Ac[3] = {-tz * Rc[1] + ty * Rc[2], tz * Rc[0] - tx * Rc[2], -ty * Rc[0] + tx * Rc[1]};
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          s_R[n * 9 + i * 3 + j] = Rc[i];
-          s_A[n * 9 + i * 3 + j] = Ac[i];
-        }
-        s_At[n * 9 + 0 + j] = kin[0] * Ac[0];
-        s_At[n * 9 + 3 + j] = kin[1] * Ac[1];
-        s_At[n * 9 + 6 + j] = kin[2] * Ac[0] + kin[3] * Ac[1] + Ac[2];
-        s_Rt[n * 9 + 0 + j] = kin[0] * Rc[0];
-        s_Rt[n * 9 + 3 + j] = kin[1] * Rc[1];
-        s_Rt[n * 9 + 6 + j] = kin[2] * Rc[0] + kin[3] * Rc[1] + Rc[2];
+      for (int i = 0; i < 3; ++i) {
+        s_R[n * 9 + i * 3 + j] = Rc[i];
+        s_A[n * 9 + i * 3 + j] = Ac[i];
       }
+      s_At[n * 9 + 0 + j] = kin[0] * Ac[0];
+      s_At[n * 9 + 3 + j] = kin[1] * Ac[1];
+      s_At[n * 9 + 6 + j] = kin[2] * Ac[0] + kin[3] * Ac[1] + Ac[2];
+      s_Rt[n * 9 + 0 + j] = kin[0] * Rc[0];
+      s_Rt[n * 9 + 3 + j] = kin[1] * Rc[1];
+      s_Rt[n * 9 + 6 + j] = kin[2] * Rc[0] + kin[3] * Rc[1] + Rc[2];
     }
     __syncthreads();
   };
@@ -669,51 +656,38 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         }
         __syncthreads();
         if (pr.dbg_clock && tid == 0) ck1a = clock64();
-        // ---- stage 2a: per-pair adjoint.  ONE warp walks the chunk's segments one after the other, 18 lanes x 2 outputs each, and
-        // adds into the per-frame slots with plain read-modify-writes (side a, then side b: a diagonal pair hits the same slots
-        // twice).  Shared-memory float atomics are compare-and-swap loops on this hardware (ATOMS.CAST.SPIN) and the segments of
-        // a CTA share frames, so one warp per segment with atomics was slower (1.4 k cycles for 3 segments; 5 k for 43). ----
-        if (warp == 0) {
+        // ---- stage 2a: per-pair adjoint, one warp per segment, 18 lanes x 2 outputs; leaves the slots zeroed ----
+        for (int sl = warp; sl < nchunk; sl += kGgsWarps) {
+          const int4 sd = s_seg[sl];
+          float* G = s_sacc + sl * kSegAcc;
+          float g3[3] = {0.f, 0.f, 0.f}, gs = 0.f;
           const int side = lane >= 9, e = (lane - side * 9) % 9, i = e / 3, j = e - i * 3;
-          float gs_sum = 0.f;  // lane 18: clamped error sum, lane 19: valid error sum (eval mode)
-          int cnt_sum = 0;     // lane 20: valid count
-          for (int sl = 0; sl < nchunk; ++sl) {
-            const int4 sd = s_seg[sl];
-            float* G = s_sacc + sl * kSegAcc;
-            float g3[3] = {0.f, 0.f, 0.f};
-            if (lane < 18) {
+          if (lane < 18) {
 #pragma unroll
-              for (int k = 0; k < 3; ++k) g3[k] = side ? G[k * 3 + i] : G[i * 3 + k];
-              if (kEval && pr.dbg_G && lane < 9) atomicAdd(&pr.dbg_G[(size_t)(cs + sl) * 9 + lane], G[lane]);
-            } else if (lane < 20) {
-              gs_sum += G[9 + (lane - 18)];
-            } else if (lane == 20) {
-              cnt_sum += s_scnt[sl];
-            }
-            __syncwarp();
-            if (lane < kSegAcc) G[lane] = 0.f;  // the segment accumulators are left zeroed for the next iteration
-            if (lane == 0) s_scnt[sl] = 0;
-            float oA = 0.f, oR = 0.f;
-            const int self = side ? sd.w : sd.z, other = side ? sd.z : sd.w;
-            if (lane < 18) pair_adjoint_entry(g3, s_At + other * 9, s_Rt + other * 9, j, &oA, &oR);
-            if (lane < 9) {
-              s_fg[self * 18 + e] += oA;
-              s_fg[self * 18 + 9 + e] += oR;
-            }
-            __syncwarp();
-            if (lane >= 9 && lane < 18) {
-              s_fg[self * 18 + e] += oA;
-              s_fg[self * 18 + 9 + e] += oR;
-            }
-            __syncwarp();
+            for (int k = 0; k < 3; ++k) g3[k] = side ? G[k * 3 + i] : G[i * 3 + k];
+            if (kEval && pr.dbg_G && lane < 9) atomicAdd(&pr.dbg_G[(size_t)(cs + sl) * 9 + lane], G[lane]);
+          } else if (lane < 20) {
+            gs = G[9 + (lane - 18)];
           }
-          if (lane == 18) s_misc[4] += gs_sum;
-          if (lane == 19 && kEval) s_misc[5] += gs_sum;
-          if (lane == 20) s_cta_cnt += cnt_sum;
+          const int cnt_seg = s_scnt[sl];
+          __syncwarp();
+          if (lane < kSegAcc) G[lane] = 0.f;
+          if (lane == 0) s_scnt[sl] = 0;
+          if (lane < 18) {
+            const int self = side ? sd.w : sd.z, other = side ? sd.z : sd.w;
+            float oA, oR;
+            pair_adjoint_entry(g3, s_At + other * 9, s_Rt + other * 9, j, &oA, &oR);
+            atomicAdd(&s_fg[self * 18 + e], oA);
+            atomicAdd(&s_fg[self * 18 + 9 + e], oR);
+          } else if (lane == 18) {
+            atomicAdd(&s_misc[4], gs);
+            atomicAdd(&s_cta_cnt, cnt_seg);
+          } else if (lane == 19 && kEval) {
+            atomicAdd(&s_misc[5], gs);
+          }
         }
       }
-      if (N > 32) __syncthreads();  // frames beyond the first warp: their threads wait for warp 0's stage 2a
-      else __syncwarp();
+      __syncthreads();
       if (pr.dbg_clock && tid == 0) ck1 = clock64();
       // ================= stage 2b: one thread per frame: unfold K, frame adjoint -> the CTA's partial gradient =================
       if (warp * 32 < N) {  // the warps that hold frames (one thread per frame)
@@ -753,7 +727,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       if (pr.dbg_clock && tid == 0) ck2 = clock64();
       // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
       ggs_exchange<kEval>(pr.xch1, pr.xch2, P.xch_mode == 1 ? pr.acc : nullptr, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
-                          cx, cy, s_gsum, s_expect, s_mine);
+                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum, s_expect, s_mine);
       ++it_global;
       __syncthreads();
       if (pr.dbg_clock && tid == 0) {
@@ -802,20 +776,20 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
             float gv[kPer];
             float gn2 = 0.f, pn2 = 0.f;
-            const int warps_used = min(kGgsWarps, (N9 + 31) / 32);  // warps that hold elements; the others skip to the barriers
-            if (warp < warps_used) {
 #pragma unroll
-              for (int q = 0; q < kPer; ++q) {
-                const int e = tid + q * kGgsThreads;
-                gv[q] = 0.f;
-                if (e < N9) {
-                  const float g1 = grad_of(e);
-                  gv[q] = g1;
-                  gn2 = fmaf(g1, g1, gn2);
-                  const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
-                  pn2 = fmaf(pm, pm, pn2);
-                }
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              gv[q] = 0.f;
+              if (e < N9) {
+                const float g1 = grad_of(e);
+                gv[q] = g1;
+                gn2 = fmaf(g1, g1, gn2);
+                const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
+                pn2 = fmaf(pm, pm, pn2);
               }
+            }
+            const int warps_used = min(kGgsWarps, (N9 + 31) / 32);  // warps that hold elements (the others contribute zeros)
+            if (warp < warps_used) {
               gn2 = warp_sum(gn2);
               pn2 = warp_sum(pn2);
               if (lane == 0) {
@@ -825,28 +799,26 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             }
             __syncthreads();
             if (pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: norm partials
-            if (warp < warps_used) {
-              gn2 = 0.f;
-              pn2 = 0.f;
-              for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
-                gn2 += s_misc[16 + wv * 2];
-                pn2 += s_misc[16 + wv * 2 + 1];
-              }
-              const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
-              const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
-              const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
+            gn2 = 0.f;
+            pn2 = 0.f;
+            for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
+              gn2 += s_misc[16 + wv * 2];
+              pn2 += s_misc[16 + wv * 2 + 1];
+            }
+            const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
+            const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
+            const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
 #pragma unroll
-              for (int q = 0; q < kPer; ++q) {
-                const int e = tid + q * kGgsThreads;
-                if (e < N9) {
-                  const float g1 = gv[q] * coef;
-                  const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
-                  s_vel[e] = v;
-                  const float pnew = s_pose[e] - P.lr * v;
-                  s_pose[e] = pnew;
-                  const int n = e / 9, c = e - n * 9;
-                  if (c >= 7) focal_of(pnew, &s_fl[n * 2 + (c - 7)], &s_inr[n * 2 + (c - 7)]);
-                }
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              if (e < N9) {
+                const float g1 = gv[q] * coef;
+                const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
+                s_vel[e] = v;
+                const float pnew = s_pose[e] - P.lr * v;
+                s_pose[e] = pnew;
+                const int n = e / 9, c = e - n * 9;
+                if (c >= 7) focal_of(pnew, &s_fl[n * 2 + (c - 7)], &s_inr[n * 2 + (c - 7)]);
               }
             }
             ++done;
