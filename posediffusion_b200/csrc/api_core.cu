@@ -20,7 +20,7 @@ struct GgsBatch {
   GgsProblem prob[kGgsBatchMax];
 };
 
-template <bool kEval, bool kPaired>
+template <bool kEval, bool kPaired, bool kProbe = false>
 __global__ void __launch_bounds__(kGgsThreads, 1)
 ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P);
 
@@ -451,15 +451,18 @@ int pdb_debug_pack_layout(const double* kp1, const double* kp2, const int64_t* i
 // GGS launch plumbing (shared with the sampler in api_sampler.cu)
 // ------------------------------------------------------------------------------------------------
 namespace {
-template <bool kEval, bool kPaired>
+template <bool kEval, bool kPaired, bool kProbe>
 __global__ void __launch_bounds__(kGgsThreads, 1)
 ggs_entry(const __grid_constant__ GgsBatch batch, const __grid_constant__ GgsParams P) {
-  ggs_body<kEval, kPaired>(batch.prob[blockIdx.x / P.ctas_per_problem], P);
+  ggs_body<kEval, kPaired, kProbe>(batch.prob[blockIdx.x / P.ctas_per_problem], P);
 }
 
-template <bool kEval, bool kPaired>
+template <bool kEval, bool kPaired, bool kProbe = false>
 int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_frames, long long max_rounds,
                      GgsParams P, cudaStream_t st) {
+  if constexpr (!kEval && !kProbe) {  // the timing probe is its own instantiation (armed by pdb_debug_ggs_clocks, single-sequence calls)
+    if (batch.prob[0].dbg_clock) return launch_ggs_chunk<kEval, kPaired, true>(ctx, batch, nprob, max_frames, max_rounds, P, st);
+  }
   const int cpp = P.ctas_per_problem;  // ggs_plan
   // shared-memory match cache: everything beyond the fixed per-frame state, in rounds of 512 B
   const size_t fixed = ggs_smem_fixed_bytes(max_frames);
@@ -471,9 +474,9 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   P.resident_rounds = resident ? (int)rounds_per_cta : 0;
   P.ring = resident ? 0 : 1;
   const size_t smem = fixed + (resident ? (size_t)rounds_per_cta * 512 : (size_t)kRingBytes);
-  size_t& attr_bytes = ctx->attr_ggs[(kEval ? 1 : 0) + (kPaired ? 2 : 0)];
+  size_t& attr_bytes = ctx->attr_ggs[(kEval ? 1 : 0) + (kPaired ? 2 : 0) + (kProbe ? 4 : 0)];
   if (smem > attr_bytes) {
-    PDB_CUDA(ctx, cudaFuncSetAttribute(ggs_entry<kEval, kPaired>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDB_CUDA(ctx, (cudaFuncSetAttribute(ggs_entry<kEval, kPaired, kProbe>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     attr_bytes = smem;
   }
   cudaLaunchConfig_t cfg = {};
@@ -488,7 +491,7 @@ int launch_ggs_chunk(Context* ctx, const GgsBatch& batch, int nprob, int max_fra
   cfg.numAttrs = 1;
   {
     ScopedTimer timer(ctx, st, 0);
-    PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ggs_entry<kEval, kPaired>, batch, P));
+    PDB_CUDA(ctx, (cudaLaunchKernelEx(&cfg, ggs_entry<kEval, kPaired, kProbe>, batch, P)));
   }
   ctx->launches += 1;
   return PDB_OK;

@@ -221,7 +221,10 @@ __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned lon
 // One CTA of the group that owns one sequence.  See the file header for the stage structure.
 // `resident_rounds` > 0: the CTA's whole slice of matches (<= resident_rounds rounds) is staged in shared memory
 // once per launch and every inner iteration streams it from there (no L2/HBM traffic inside the loop).
-template <bool kEval, bool kPaired = false>
+// kProbe: the stage timing probe (tools/ggs_stage_probe.py) is a separate instantiation, so that the production kernels carry no
+// clock reads: the code one iteration executes (1 871 instructions = 255 lines of 128 B with the probe) sits right at the 32 KB
+// capacity of the L1.5 instruction cache (hit rate 85 %, profiles/r2_ggs_cfg3_ncu_raw.csv).
+template <bool kEval, bool kPaired = false, bool kProbe = false>
 __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& P) {
 #ifdef PDB_EMU  // tests/host/cuda_emu.h (CPU emulation of this kernel, test harness only): dynamic shared memory of this CTA
   unsigned char* const smem_raw = emu::g_cta->smem;
@@ -397,7 +400,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
     float last_logged = __int_as_float(0x7fc00000);
     for (int iter = 0; iter < iters; ++iter) {
       long long ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck1a = 0;  // stage timing probe (thread 0; the sums are flushed once per launch)
-      if (pr.dbg_clock && tid == 0) ck0 = clock64();
+      if (kProbe && pr.dbg_clock && tid == 0) ck0 = clock64();
       // ================= chunks of <= kGgsMaxSeg pair segments (one chunk in all practical cases) =================
       for (int cs = seg_lo; cs <= seg_hi; cs += kGgsMaxSeg) {
         const int ce = min(cs + kGgsMaxSeg, seg_hi + 1);
@@ -655,7 +658,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
           }
         }
         __syncthreads();
-        if (pr.dbg_clock && tid == 0) ck1a = clock64();
+        if (kProbe && pr.dbg_clock && tid == 0) ck1a = clock64();
         // ---- stage 2a: per-pair adjoint, one warp per segment, 18 lanes x 2 outputs; leaves the slots zeroed ----
         for (int sl = warp; sl < nchunk; sl += kGgsWarps) {
           const int4 sd = s_seg[sl];
@@ -688,18 +691,15 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         }
       }
       __syncthreads();
-      if (pr.dbg_clock && tid == 0) ck1 = clock64();
+      if (kProbe && pr.dbg_clock && tid == 0) ck1 = clock64();
       // ================= stage 2b: one thread per frame: unfold K, frame adjoint -> the CTA's partial gradient =================
       if (warp * 32 < N) {  // the warps that hold frames (one thread per frame)
         const int n = tid;
         float k4[4] = {0.f, 0.f, 0.f, 0.f};
         if (n < N) {
           float* gAt = s_fg + n * 18;
-          bool touched = false;
-#pragma unroll
-          for (int k = 0; k < 18; ++k) touched |= (gAt[k] != 0.f);
           float gT[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-          if (touched) {
+          if (s_mine[n]) {  // the frames this CTA's segments touch (static plan); all other slots stay zero
             float gA[9], gR[9];
             frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
             frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
@@ -724,13 +724,13 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         }
       }
       __syncthreads();
-      if (pr.dbg_clock && tid == 0) ck2 = clock64();
+      if (kProbe && pr.dbg_clock && tid == 0) ck2 = clock64();
       // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
       ggs_exchange<kEval>(pr.xch1, pr.xch2, P.xch_mode == 1 ? pr.acc : nullptr, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
                           (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum, s_expect, s_mine);
       ++it_global;
       __syncthreads();
-      if (pr.dbg_clock && tid == 0) {
+      if (kProbe && pr.dbg_clock && tid == 0) {
         ck3 = clock64();
         clk_sum[1] += ck1a - ck0; clk_sum[4] += ck1 - ck1a; clk_sum[2] += ck2 - ck1; clk_sum[3] += ck3 - ck2; clk_sum[5] += 1;
       }
@@ -798,7 +798,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               }
             }
             __syncthreads();
-            if (pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: norm partials
+            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: norm partials
             gn2 = 0.f;
             pn2 = 0.f;
             for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
@@ -823,12 +823,12 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
             }
             ++done;
             __syncthreads();
-            if (pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[7] += c - ck3; ck3 = c; }  // probe: coefficient + update
+            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[7] += c - ck3; ck3 = c; }  // probe: coefficient + update
             frames_forward();  // stage 0 of the next iteration (one block barrier inside)
           }
         }
       }
-      if (pr.dbg_clock && tid == 0) clk_sum[6] += clock64() - ck3;
+      if (kProbe && pr.dbg_clock && tid == 0) clk_sum[6] += clock64() - ck3;
       if (kEval) break;
       if (drop_phase) break;  // uniform: phase dropped on "insufficient valid matches" (no update, :103-108)
     }
@@ -840,7 +840,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       pr.stats->n_valid[phase] = last_valid;
     }
   }
-  if (pr.dbg_clock && tid == 0)
+  if (kProbe && pr.dbg_clock && tid == 0)
     for (int k = 0; k < 8; ++k) pr.dbg_clock[(size_t)cta * 8 + k] += clk_sum[k];
   if (!kEval && cta == 0) {
     for (int e = tid; e < N9; e += kGgsThreads) pr.pose[e] = s_pose[e];
