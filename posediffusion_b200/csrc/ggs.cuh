@@ -262,7 +262,6 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   const long long R = pr.rounds;
   int r_cta0, r_cta1, r_w0, r_w1;  // paired layout: all four are even (whole units of two rounds)
   ggs_cta_range(R, cta, cpp, kPaired, &r_cta0, &r_cta1);
-  ggs_warp_range(r_cta0, r_cta1, warp, kGgsWarps, kPaired, &r_w0, &r_w1);
   auto seg_of_round = [&](int r) {  // last segment whose first_round <= r
     int lo = 0, hi = pr.nseg;       // segs[nseg].x == rounds > r
     while (hi - lo > 1) {
@@ -274,6 +273,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   const bool cta_has_work = r_cta1 > r_cta0;
   const int seg_lo = cta_has_work ? seg_of_round(r_cta0) : 0;
   const int seg_hi = cta_has_work ? seg_of_round(r_cta1 - 1) : -1;  // inclusive
+  ggs_warp_range_seg(pr.segs, seg_lo, seg_hi, r_cta0, r_cta1, warp, kGgsWarps, kPaired, &r_w0, &r_w1);  // no warp crosses a segment
   const int wseg0 = (r_w1 > r_w0) ? seg_of_round(r_w0) : 0;
   const bool single_chunk = (seg_hi - seg_lo + 1) <= kGgsMaxSeg;
   const bool resident = (r_cta1 - r_cta0) <= P.resident_rounds;

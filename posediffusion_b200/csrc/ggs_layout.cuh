@@ -59,6 +59,41 @@ PDB_HD void ggs_warp_range(int r_cta0, int r_cta1, int warp, int nwarps, bool pa
   }
 }
 
+// Segment-aware warp partition: rounds [r0, r1) of warp `warp` inside the CTA range [r_cta0, r_cta1), which intersects the pair
+// segments seg_lo..seg_hi (segs[s].x = first round of segment s; segs[nseg].x = total rounds).  The CTA's warps are first
+// distributed over those segments -- one each, the rest greedily to the segment with the largest share per warp -- and the
+// part of a segment inside the CTA is then split evenly among its warps, so that NO warp crosses a segment boundary: every
+// (warp, segment) visit costs an F' set-up and a 16-shuffle reduction, and the warps that paid two of them were the stragglers
+// of stage 1.  Falls back to the even split when the CTA touches more segments than it has warps.
+PDB_HD void ggs_warp_range_seg(const int4* segs, int seg_lo, int seg_hi, int r_cta0, int r_cta1, int warp, int nwarps, bool paired,
+                               int* r0, int* r1) {
+  const int nseg_c = seg_hi - seg_lo + 1;
+  if (r_cta1 <= r_cta0 || nseg_c < 1 || nseg_c > nwarps || nwarps > 16) {
+    ggs_warp_range(r_cta0, r_cta1, warp, nwarps, paired, r0, r1);
+    return;
+  }
+  const int g = paired ? 2 : 1;  // granule: whole units in the paired layout (segments and CTA ranges start on even rounds)
+  int share[16], wcount[16];
+  for (int k = 0; k < nseg_c; ++k) {
+    const int lo = segs[seg_lo + k].x > r_cta0 ? segs[seg_lo + k].x : r_cta0;
+    const int hi = segs[seg_lo + k + 1].x < r_cta1 ? segs[seg_lo + k + 1].x : r_cta1;
+    share[k] = (hi - lo) / g;
+    wcount[k] = 1;
+  }
+  for (int extra = nwarps - nseg_c; extra > 0; --extra) {  // next warp to the segment with the largest share per warp (first wins ties)
+    int best = 0;
+    for (int k = 1; k < nseg_c; ++k)
+      if ((long long)share[k] * wcount[best] > (long long)share[best] * wcount[k]) best = k;
+    wcount[best] += 1;
+  }
+  int k = 0, base = 0;
+  while (warp >= base + wcount[k]) base += wcount[k++];
+  const int idx = warp - base;
+  const int lo = segs[seg_lo + k].x > r_cta0 ? segs[seg_lo + k].x : r_cta0;
+  *r0 = lo + g * (int)((long long)share[k] * idx / wcount[k]);
+  *r1 = lo + g * (int)((long long)share[k] * (idx + 1) / wcount[k]);
+}
+
 // upper bound of the rounds one CTA can own (sizes the shared-memory match cache)
 PDB_HD long long ggs_rounds_per_cta(long long max_rounds, int cpp, bool paired) {
   if (paired) return 2 * (((max_rounds >> 1) + cpp - 1) / cpp);

@@ -126,7 +126,7 @@ extern "C" int geom_host_eval_folded(const float* pose, int N, float height, flo
 
 // ---------------------------------------------------------------------------------------------------------------
 // Stage-1 traversal of the GGS kernel (csrc/ggs.cuh), replayed sequentially: CTA / warp partition (the kernel's own
-// ggs_cta_range / ggs_warp_range), pair-segment switches, the ring / resident / register-stream walks with their
+// ggs_cta_range / ggs_warp_range_seg), pair-segment switches, the ring / resident / register-stream walks with their
 // fast-path conditions and in-bounds tests, for the plain and the paired stream layouts (csrc/ggs_layout.cuh).
 // It checks the INDEXING contract of a layout without a GPU: which row of the stream image is read as which match of
 // which segment.  Lanes are a loop; shuffles / barriers / atomics have no counterpart here.
@@ -219,7 +219,7 @@ extern "C" int ggs_host_walk(const float* pts, const int* segs, int nseg, long l
     const bool resident = mode == 0;
     for (int warp = 0; warp < kWalkWarps; ++warp) {
       int r_w0, r_w1;
-      ggs_warp_range(r_cta0, r_cta1, warp, kWalkWarps, w.paired, &r_w0, &r_w1);
+      ggs_warp_range_seg(w.segs, seg_lo, seg_hi, r_cta0, r_cta1, warp, kWalkWarps, w.paired, &r_w0, &r_w1);
       if (w.paired && ((r_w0 | r_w1 | r_cta0 | r_cta1) & 1)) return -4;
       const int wseg0 = (r_w1 > r_w0) ? w.seg_of_round(r_w0) : 0;
       for (int cs = seg_lo; cs <= seg_hi; cs += kWalkMaxSeg) {
