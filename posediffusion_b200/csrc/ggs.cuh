@@ -76,7 +76,7 @@ constexpr int kAccStride = 32;  // floats between two accumulators: one 128-byte
 __host__ __device__ inline int ggs_xch_words(int frames) { return frames * 7 + kAccTail; }
 __host__ __device__ inline int ggs_xch_groups(int cpp, int group) { return group >= cpp ? 0 : (cpp + group - 1) / group; }
 
-constexpr int kGgsFixedFloatsPerFrame = 2 * 9 + 4 * 9 + 4 + 18 + 14;  // pose, vel, R, A, Rt, At, fl, inr, gAt|gRt, partial + summed gradient
+constexpr int kGgsFixedFloatsPerFrame = 2 * 22 + 4 * 9 + 18 + 14;  // 2 x {pose, vel, fl, inr}, R, A, Rt, At, gAt|gRt, partial + summed gradient
 
 __host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
   size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 128 + (size_t)kGgsMaxSeg * kSegAcc);
@@ -239,15 +239,22 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
 
   // ---- shared memory carve-up ----
   int4* s_seg = reinterpret_cast<int4*>(smem_raw);
+  // optimiser state {pose, momentum buffer, clamped focal lengths, clamp mask}: two copies -- the step reads the current one
+  // and writes the next one (several warps finish the step redundantly and must not see each other's updates), then they swap
+  const int state_floats = 22 * N;
   float* s_pose = reinterpret_cast<float*>(s_seg + kGgsMaxSeg + 1);
   float* s_vel = s_pose + N9;
-  float* s_R = s_vel + N9;
+  float* s_fl = s_vel + N9;         // clamped focal lengths [N][2]
+  float* s_inr = s_fl + 2 * N;      // 1 where the clamp passes gradient
+  float* s_pose_nxt = s_pose + state_floats;
+  float* s_vel_nxt = s_vel + state_floats;
+  float* s_fl_nxt = s_fl + state_floats;
+  float* s_inr_nxt = s_inr + state_floats;
+  float* s_R = s_pose + 2 * state_floats;
   float* s_A = s_R + N9;
   float* s_Rt = s_A + N9;
   float* s_At = s_Rt + N9;
-  float* s_fl = s_At + N9;          // clamped focal lengths [N][2]
-  float* s_inr = s_fl + 2 * N;      // 1 where the clamp passes gradient
-  float* s_fg = s_inr + 2 * N;      // [N][18]: gAt (0..8), gRt (9..17)
+  float* s_fg = s_At + N9;          // [N][18]: gAt (0..8), gRt (9..17)
   float* s_misc = s_fg + 2 * N9;    // [4] clamp_sum, [5] loss_sum, [8..11] sum over frames of d/d(ix, iy, kx, ky), [16..47] norm partials
   float* s_part = s_misc + 64;      // [N*7] this CTA's partial gradient of the iteration
   float* s_gsum = s_part + N * 7 + 32;  // [N*7 + kAccTail] summed gradient of this iteration (all CTAs: identical bits)
@@ -343,23 +350,12 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
     *fl = fminf(fmaxf(ev, kFlMin), kFlMax);
     *inr = (ev >= kFlMin && ev <= kFlMax) ? 1.f : 0.f;
   };
-  auto frames_forward = [&]() {
-    {  // shared focal length = mean over frames (geometry_guided_sampling.py:142), reduced redundantly per warp
-      float fx = 0.f, fy = 0.f;
-      for (int m = lane; m < N; m += 32) {
-        fx += s_fl[m * 2];
-        fy += s_fl[m * 2 + 1];
-      }
-      fpx = warp_sum(fx) * scale_over_N;
-      fpy = warp_sum(fy) * scale_over_N;
-      kin[0] = 1.f / fpx;
-      kin[1] = 1.f / fpy;
-      kin[2] = -cx * kin[0];
-      kin[3] = -cy * kin[1];
-    }
+  // K-folded per-frame terms of the frame this thread co-owns (thread (n, j < 3) builds column j), from `pose` and the shared
+  // intrinsics kin of the calling warp
+  auto frame_columns = [&](const float* pose) {
     const int n = tid >> 2, j = tid & 3;
     if (n < N && j < 3) {
-      const float* p = s_pose + n * 9;
+      const float* p = pose + n * 9;
       const float w = p[3], x = p[4], y = p[5], z = p[6];
       const float s2 = 2.0f / (w * w + x * x + y * y + z * z);
       // row j of the pytorch3d rotation = column j of R_cv up to the signs D = diag(-1,-1,1) on the rows
@@ -382,6 +378,27 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       s_Rt[n * 9 + 3 + j] = kin[1] * Rc[1];
       s_Rt[n * 9 + 6 + j] = kin[2] * Rc[0] + kin[3] * Rc[1] + Rc[2];
     }
+  };
+  // Pose -> per-frame terms at the start of the launch (inside the loop the step does this itself, see stage 3)
+  auto frames_forward = [&]() {
+    if (warp * 32 < 4 * N) {
+      float fx = 0.f, fy = 0.f;
+      for (int m = lane; m < N; m += 32) {
+        fx += s_fl[m * 2];
+        fy += s_fl[m * 2 + 1];
+      }
+      fpx = warp_sum(fx) * scale_over_N;
+      fpy = warp_sum(fy) * scale_over_N;
+      kin[0] = 1.f / fpx;
+      kin[1] = 1.f / fpy;
+      kin[2] = -cx * kin[0];
+      kin[3] = -cy * kin[1];
+      if (tid == 0) {
+        s_misc[12] = fpx;
+        s_misc[13] = fpy;
+      }
+      frame_columns(s_pose);
+    }
     __syncthreads();
   };
   static_assert(4 * kMaxFrames <= kGgsThreads, "four threads per frame");
@@ -390,7 +407,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   __syncthreads();
   frames_forward();
 
-  __shared__ long long clk_sum[8];  // probe (thread 0): {stage 3 norms, stage 1, stage 2b, exchange, stage 2a, iterations, next stage 0, stage 3 update}
+  __shared__ long long clk_sum[8];  // probe (thread 0): {-, stage 1, stage 2b, exchange, stage 2a, iterations, step + next stage 0, -}
   if (tid < 8) clk_sum[tid] = 0;
   for (int phase = 0; phase < P.n_phases; ++phase) {
     const int flags = P.flags[phase];
@@ -727,7 +744,8 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       if (kProbe && pr.dbg_clock && tid == 0) ck2 = clock64();
       // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
       ggs_exchange<kEval>(pr.xch1, pr.xch2, P.xch_mode == 1 ? pr.acc : nullptr, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
-                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum, s_expect, s_mine);
+                          (-s_misc[8] + cx * s_misc[10]) / (s_misc[12] * s_misc[12]), (-s_misc[9] + cy * s_misc[11]) / (s_misc[13] * s_misc[13]), s_gsum,
+                          s_expect, s_mine);  // s_misc[12..13] = f'x, f'y of the current pose (written with the per-frame terms)
       ++it_global;
       __syncthreads();
       if (kProbe && pr.dbg_clock && tid == 0) {
@@ -772,59 +790,71 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               }
             }
           } else {
-            // clip norms: one element per thread (N9 <= 1152: up to three), warp sums, partials through shared memory
-            constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
-            float gv[kPer];
-            float gn2 = 0.f, pn2 = 0.f;
-#pragma unroll
-            for (int q = 0; q < kPer; ++q) {
-              const int e = tid + q * kGgsThreads;
-              gv[q] = 0.f;
-              if (e < N9) {
+            // The warps that hold (frame, column) threads -- 8 frames each, 3 warps at N = 20 -- finish the step REDUNDANTLY and
+            // go straight on to stage 0 of the next iteration for their own frames; everybody else waits at the one block
+            // barrier at the end.  (Three block barriers -- norm partials, updated pose, per-frame terms -- cost 1.4 + 1.1 + 1.6 k
+            // cycles for a few hundred flops.)  All reads come from the current state copy, all writes go to the next one.
+            if (warp * 32 < 4 * N) {
+              float gn2 = 0.f, pn2 = 0.f;  // clip norms over ALL elements: lane-strided, then an xor butterfly (same bits in every warp)
+              for (int e = lane; e < N9; e += 32) {
                 const float g1 = grad_of(e);
-                gv[q] = g1;
                 gn2 = fmaf(g1, g1, gn2);
                 const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
                 pn2 = fmaf(pm, pm, pn2);
               }
-            }
-            const int warps_used = min(kGgsWarps, (N9 + 31) / 32);  // warps that hold elements (the others contribute zeros)
-            if (warp < warps_used) {
               gn2 = warp_sum(gn2);
               pn2 = warp_sum(pn2);
-              if (lane == 0) {
-                s_misc[16 + warp * 2] = gn2;
-                s_misc[16 + warp * 2 + 1] = pn2;
-              }
-            }
-            __syncthreads();
-            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: norm partials
-            gn2 = 0.f;
-            pn2 = 0.f;
-            for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
-              gn2 += s_misc[16 + wv * 2];
-              pn2 += s_misc[16 + wv * 2 + 1];
-            }
-            const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
-            const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
-            const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
-#pragma unroll
-            for (int q = 0; q < kPer; ++q) {
-              const int e = tid + q * kGgsThreads;
-              if (e < N9) {
-                const float g1 = gv[q] * coef;
-                const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
-                s_vel[e] = v;
+              const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
+              const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
+              const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
+              const bool first = done == 0;                            // momentum buffer resets per phase
+              const int f_lo = warp * 8, f_hi = min(N, f_lo + 8);      // the frames whose state this warp writes
+              // focal lengths of ALL frames (their mean is shared), stored for the own frames only
+              float fx = 0.f, fy = 0.f;
+              for (int m = lane; m < 2 * N; m += 32) {
+                const int n = m >> 1, e = n * 9 + 7 + (m & 1);
+                const float g1 = grad_of(e) * coef;
+                const float v = first ? g1 : fmaf(P.momentum, s_vel[e], g1);
                 const float pnew = s_pose[e] - P.lr * v;
-                s_pose[e] = pnew;
-                const int n = e / 9, c = e - n * 9;
-                if (c >= 7) focal_of(pnew, &s_fl[n * 2 + (c - 7)], &s_inr[n * 2 + (c - 7)]);
+                float fl, inr;
+                focal_of(pnew, &fl, &inr);
+                if (m & 1) fy += fl; else fx += fl;
+                if (n >= f_lo && n < f_hi) {
+                  s_vel_nxt[e] = v;
+                  s_pose_nxt[e] = pnew;
+                  s_fl_nxt[m] = fl;
+                  s_inr_nxt[m] = inr;
+                }
               }
+              fpx = warp_sum(fx) * scale_over_N;  // shared focal length = mean over frames (geometry_guided_sampling.py:142)
+              fpy = warp_sum(fy) * scale_over_N;
+              kin[0] = 1.f / fpx;
+              kin[1] = 1.f / fpy;
+              kin[2] = -cx * kin[0];
+              kin[3] = -cy * kin[1];
+              if (tid == 0) {
+                s_misc[12] = fpx;
+                s_misc[13] = fpy;
+              }
+              // translation and quaternion of the own frames
+              for (int i = lane; i < (f_hi - f_lo) * 7; i += 32) {
+                const int n = f_lo + i / 7, e = n * 9 + (i - (i / 7) * 7);
+                const float g1 = grad_of(e) * coef;
+                const float v = first ? g1 : fmaf(P.momentum, s_vel[e], g1);
+                s_vel_nxt[e] = v;
+                s_pose_nxt[e] = s_pose[e] - P.lr * v;
+              }
+              __syncwarp();
+              frame_columns(s_pose_nxt);  // stage 0 of the next iteration for the own frames
             }
             ++done;
+            {  // the next state becomes the current one (uniform: every thread swaps its pointers)
+              float* t0 = s_pose; s_pose = s_pose_nxt; s_pose_nxt = t0;
+              float* t1 = s_vel; s_vel = s_vel_nxt; s_vel_nxt = t1;
+              float* t2 = s_fl; s_fl = s_fl_nxt; s_fl_nxt = t2;
+              float* t3 = s_inr; s_inr = s_inr_nxt; s_inr_nxt = t3;
+            }
             __syncthreads();
-            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[7] += c - ck3; ck3 = c; }  // probe: coefficient + update
-            frames_forward();  // stage 0 of the next iteration (one block barrier inside)
           }
         }
       }
