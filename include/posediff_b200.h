@@ -89,7 +89,7 @@ int pdb_profile_enable(pdb_context* ctx, int32_t on);
 int pdb_profile_read(pdb_context* ctx, double* ggs_ms, int64_t* ggs_launches, double* denoiser_ms, int64_t* denoiser_launches);
 
 /* Debug probe (not part of the reference surface): per-CTA cycle sums of a persistent kernel's stages.  enable = 1: the GGS kernel
- * of single-sequence calls, out[cta][8] = {-, stage1, stage2b, exchange, stage2a, iterations, step + next stage 0, -};
+ * of single-sequence calls, out[cta][8] = {stage3 norms, stage1, stage2b, exchange, stage2a, iterations, next stage 0, stage3 update};
  * enable = 2: the fp32 denoiser kernel, out[cta][8] = {barrier, tile load + LayerNorm, linear item, attention, tail, steps, -, -};
  * enable = 0 frees the buffer. */
 int pdb_debug_ggs_clocks(pdb_context* ctx, int32_t enable, int64_t* out, int32_t max_ctas);

@@ -141,7 +141,7 @@ int pdb_profile_read(pdb_context* c, double* ggs_ms, int64_t* ggs_launches, doub
   return PDB_OK;
 }
 
-// Debug probe: per-CTA cycle sums of the GGS stages {-, stage1, stage2b, exchange, stage2a, iterations, step + next stage 0, -} (enable = 1) or of
+// Debug probe: per-CTA cycle sums of the GGS stages {stage3 norms, stage1, stage2b, exchange, stage2a, iterations, next stage 0, stage3 update} (enable = 1) or of
 // the fp32 denoiser kernel {barrier, tile load + LayerNorm, linear item, attention, tail, steps} (enable = 2).
 int pdb_debug_ggs_clocks(pdb_context* c, int32_t enable, int64_t* out, int32_t max_ctas) {
   if (!c) return PDB_ERR_INVALID;

@@ -76,10 +76,10 @@ constexpr int kAccStride = 32;  // floats between two accumulators: one 128-byte
 __host__ __device__ inline int ggs_xch_words(int frames) { return frames * 7 + kAccTail; }
 __host__ __device__ inline int ggs_xch_groups(int cpp, int group) { return group >= cpp ? 0 : (cpp + group - 1) / group; }
 
-constexpr int kGgsFixedFloatsPerFrame = 2 * 22 + 4 * 9 + 18 + 14;  // 2 x {pose, vel, fl, inr}, R, A, Rt, At, gAt|gRt, partial + summed gradient
+constexpr int kGgsFixedFloatsPerFrame = 2 * 9 + 4 * 9 + 4 + 18 + 14;  // pose, vel, R, A, Rt, At, fl, inr, gAt|gRt, partial + summed gradient
 
 __host__ __device__ inline size_t ggs_smem_fixed_bytes(int frames) {
-  size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 160 + (size_t)kGgsMaxSeg * kSegAcc);
+  size_t bytes = sizeof(float) * ((size_t)frames * kGgsFixedFloatsPerFrame + 128 + (size_t)kGgsMaxSeg * kSegAcc);
   bytes += kGgsMaxSeg * sizeof(int);         // segment valid counts
   bytes += 2 * (size_t)frames * sizeof(int);  // exchange plan: contributors per frame, own frames
   bytes += (kGgsMaxSeg + 1) * sizeof(int4);  // segment descriptors
@@ -239,24 +239,17 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
 
   // ---- shared memory carve-up ----
   int4* s_seg = reinterpret_cast<int4*>(smem_raw);
-  // optimiser state {pose, momentum buffer, clamped focal lengths, clamp mask}: two copies -- the step reads the current one
-  // and writes the next one (several warps finish the step redundantly and must not see each other's updates), then they swap
-  const int state_floats = 22 * N;
   float* s_pose = reinterpret_cast<float*>(s_seg + kGgsMaxSeg + 1);
   float* s_vel = s_pose + N9;
-  float* s_fl = s_vel + N9;         // clamped focal lengths [N][2]
-  float* s_inr = s_fl + 2 * N;      // 1 where the clamp passes gradient
-  float* s_pose_nxt = s_pose + state_floats;
-  float* s_vel_nxt = s_vel + state_floats;
-  float* s_fl_nxt = s_fl + state_floats;
-  float* s_inr_nxt = s_inr + state_floats;
-  float* s_R = s_pose + 2 * state_floats;
+  float* s_R = s_vel + N9;
   float* s_A = s_R + N9;
   float* s_Rt = s_A + N9;
   float* s_At = s_Rt + N9;
-  float* s_fg = s_At + N9;          // [N][18]: gAt (0..8), gRt (9..17)
-  float* s_misc = s_fg + 2 * N9;    // [4] clamp_sum, [5] loss_sum, [12..13] f'x, f'y, [16 + 4 w ..] d/d(ix, iy, kx, ky) summed over the frames of warp w
-  float* s_part = s_misc + 96;      // [N*7] this CTA's partial gradient of the iteration
+  float* s_fl = s_At + N9;          // clamped focal lengths [N][2]
+  float* s_inr = s_fl + 2 * N;      // 1 where the clamp passes gradient
+  float* s_fg = s_inr + 2 * N;      // [N][18]: gAt (0..8), gRt (9..17)
+  float* s_misc = s_fg + 2 * N9;    // [4] clamp_sum, [5] loss_sum, [8..11] sum over frames of d/d(ix, iy, kx, ky), [16..47] norm partials
+  float* s_part = s_misc + 64;      // [N*7] this CTA's partial gradient of the iteration
   float* s_gsum = s_part + N * 7 + 32;  // [N*7 + kAccTail] summed gradient of this iteration (all CTAs: identical bits)
   float* s_sacc = s_gsum + N * 7 + 32;  // [kGgsMaxSeg][kSegAcc]
   int* s_scnt = reinterpret_cast<int*>(s_sacc + kGgsMaxSeg * kSegAcc);
@@ -302,7 +295,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   for (int e = tid; e < 2 * N9; e += kGgsThreads) s_fg[e] = 0.f;
   for (int e = tid; e < kGgsMaxSeg * kSegAcc; e += kGgsThreads) s_sacc[e] = 0.f;
   for (int e = tid; e < kGgsMaxSeg; e += kGgsThreads) s_scnt[e] = 0;
-  if (tid < 96) s_misc[tid] = 0.f;
+  if (tid < 64) s_misc[tid] = 0.f;
   if (tid == 0) s_cta_cnt = 0;
   if (single_chunk && cta_has_work && tid <= seg_hi - seg_lo + 1) s_seg[tid] = __ldg(&pr.segs[seg_lo + tid]);
   if (resident) {
@@ -350,12 +343,23 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
     *fl = fminf(fmaxf(ev, kFlMin), kFlMax);
     *inr = (ev >= kFlMin && ev <= kFlMax) ? 1.f : 0.f;
   };
-  // K-folded per-frame terms of the frame this thread co-owns (thread (n, j < 3) builds column j), from `pose` and the shared
-  // intrinsics kin of the calling warp
-  auto frame_columns = [&](const float* pose) {
+  auto frames_forward = [&]() {
+    {  // shared focal length = mean over frames (geometry_guided_sampling.py:142), reduced redundantly per warp
+      float fx = 0.f, fy = 0.f;
+      for (int m = lane; m < N; m += 32) {
+        fx += s_fl[m * 2];
+        fy += s_fl[m * 2 + 1];
+      }
+      fpx = warp_sum(fx) * scale_over_N;
+      fpy = warp_sum(fy) * scale_over_N;
+      kin[0] = 1.f / fpx;
+      kin[1] = 1.f / fpy;
+      kin[2] = -cx * kin[0];
+      kin[3] = -cy * kin[1];
+    }
     const int n = tid >> 2, j = tid & 3;
     if (n < N && j < 3) {
-      const float* p = pose + n * 9;
+      const float* p = s_pose + n * 9;
       const float w = p[3], x = p[4], y = p[5], z = p[6];
       const float s2 = 2.0f / (w * w + x * x + y * y + z * z);
       // row j of the pytorch3d rotation = column j of R_cv up to the signs D = diag(-1,-1,1) on the rows
@@ -378,27 +382,6 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       s_Rt[n * 9 + 3 + j] = kin[1] * Rc[1];
       s_Rt[n * 9 + 6 + j] = kin[2] * Rc[0] + kin[3] * Rc[1] + Rc[2];
     }
-  };
-  // Pose -> per-frame terms at the start of the launch (inside the loop the step does this itself, see stage 3)
-  auto frames_forward = [&]() {
-    if (warp * 32 < 4 * N) {
-      float fx = 0.f, fy = 0.f;
-      for (int m = lane; m < N; m += 32) {
-        fx += s_fl[m * 2];
-        fy += s_fl[m * 2 + 1];
-      }
-      fpx = warp_sum(fx) * scale_over_N;
-      fpy = warp_sum(fy) * scale_over_N;
-      kin[0] = 1.f / fpx;
-      kin[1] = 1.f / fpy;
-      kin[2] = -cx * kin[0];
-      kin[3] = -cy * kin[1];
-      if (tid == 0) {
-        s_misc[12] = fpx;
-        s_misc[13] = fpy;
-      }
-      frame_columns(s_pose);
-    }
     __syncthreads();
   };
   static_assert(4 * kMaxFrames <= kGgsThreads, "four threads per frame");
@@ -407,7 +390,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
   __syncthreads();
   frames_forward();
 
-  __shared__ long long clk_sum[8];  // probe (thread 0): {-, stage 1, stage 2b, exchange, stage 2a, iterations, step + next stage 0, -}
+  __shared__ long long clk_sum[8];  // probe (thread 0): {stage 3 norms, stage 1, stage 2b, exchange, stage 2a, iterations, next stage 0, stage 3 update}
   if (tid < 8) clk_sum[tid] = 0;
   for (int phase = 0; phase < P.n_phases; ++phase) {
     const int flags = P.flags[phase];
@@ -709,88 +692,19 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       }
       __syncthreads();
       if (kProbe && pr.dbg_clock && tid == 0) ck1 = clock64();
-      // ================= stage 2b: unfold K, frame adjoint -> the CTA's partial gradient.  Four lanes per frame (thread (n, j):
-      // column j < 3 of the 3x3 terms, j = 3 idle), sums over the columns with two xor shuffles: a third of the serial
-      // instruction count of one thread per frame (this warp is the critical path between two block barriers) =================
-      if (warp * 32 < 4 * N) {
-        const int n = tid >> 2, j = tid & 3;
-        float pq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // column partials of gB, dw, dx, dy, dz, gt0, gt1, gt2
-        float k4[4] = {0.f, 0.f, 0.f, 0.f};                       // column partials of d/d(ix, iy, kx, ky)
-        float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
-        const bool mine = n < N && s_mine[n] != 0;  // static plan: the frames this CTA's segments touch
+      // ================= stage 2b: one thread per frame: unfold K, frame adjoint -> the CTA's partial gradient =================
+      if (warp * 32 < N) {  // the warps that hold frames (one thread per frame)
+        const int n = tid;
+        float k4[4] = {0.f, 0.f, 0.f, 0.f};
         if (n < N) {
-          const float* p = s_pose + n * 9;
-          qw = p[3]; qx = p[4]; qy = p[5]; qz = p[6];
-          if (mine && j < 3) {
-            float* gAt = s_fg + n * 18;
-            const float at0 = gAt[0 + j], at1 = gAt[3 + j], at2 = gAt[6 + j];
-            const float rt0 = gAt[9 + j], rt1 = gAt[12 + j], rt2 = gAt[15 + j];
-            gAt[0 + j] = 0.f; gAt[3 + j] = 0.f; gAt[6 + j] = 0.f;  // the per-frame slots are left zeroed for the next iteration
-            gAt[9 + j] = 0.f; gAt[12 + j] = 0.f; gAt[15 + j] = 0.f;
-            const float* Am = s_A + n * 9;
-            const float* Rm = s_R + n * 9;
-            const float a0 = Am[0 + j], a1 = Am[3 + j];
-            const float r0 = Rm[0 + j], r1 = Rm[3 + j], r2 = Rm[6 + j];
-            // unfold K (column j of gA, gR) and the column's share of the intrinsics' adjoint (geom.cuh frame_unfold)
-            const float gA0 = kin[0] * at0 + kin[2] * at2, gA1 = kin[1] * at1 + kin[3] * at2, gA2 = at2;
-            const float gR0 = kin[0] * rt0 + kin[2] * rt2, gR1 = kin[1] * rt1 + kin[3] * rt2, gR2 = rt2;
-            k4[0] = a0 * at0 + r0 * rt0;
-            k4[1] = a1 * at1 + r1 * rt1;
-            k4[2] = a0 * at2 + r0 * rt2;
-            k4[3] = a1 * at2 + r1 * rt2;
-            // frame adjoint (geom.cuh frame_adjoint): column j of gRcv = gR - hat(t) gA, i.e. row j of g = D gRcv^T
-            const float tx = -p[0], ty = -p[1], tz = p[2];
-            const float h0 = -(gR0 - (-tz * gA1 + ty * gA2));
-            const float h1 = -(gR1 - (tz * gA0 - tx * gA2));
-            const float h2 = gR2 - (-ty * gA0 + tx * gA1);
-            // gt = (W21 - W12, W02 - W20, W10 - W01) with W = gA R^T summed over the columns
-            pq[5] = gA2 * r1 - gA1 * r2;
-            pq[6] = gA0 * r2 - gA2 * r0;
-            pq[7] = gA1 * r0 - gA0 * r1;
-            // row j of B(q) and of the four derivative patterns d B / d(w, x, y, z)
-            const float w = qw, x = qx, y = qy, z = qz;
-            float b0, b1, b2, w0, w1, w2, x0, x1, x2, y0, y1, y2, z0, z1, z2;
-            if (j == 0) {
-              b0 = -(y * y + z * z); b1 = x * y - z * w; b2 = x * z + y * w;
-              w0 = 0.f; w1 = -z; w2 = y;
-              x0 = 0.f; x1 = y; x2 = z;
-              y0 = -2.f * y; y1 = x; y2 = w;
-              z0 = -2.f * z; z1 = -w; z2 = x;
-            } else if (j == 1) {
-              b0 = x * y + z * w; b1 = -(x * x + z * z); b2 = y * z - x * w;
-              w0 = z; w1 = 0.f; w2 = -x;
-              x0 = y; x1 = -2.f * x; x2 = -w;
-              y0 = x; y1 = 0.f; y2 = z;
-              z0 = w; z1 = -2.f * z; z2 = y;
-            } else {
-              b0 = x * z - y * w; b1 = y * z + x * w; b2 = -(x * x + y * y);
-              w0 = -y; w1 = x; w2 = 0.f;
-              x0 = z; x1 = w; x2 = -2.f * x;
-              y0 = -w; y1 = z; y2 = -2.f * y;
-              z0 = x; z1 = y; z2 = 0.f;
-            }
-            pq[0] = h0 * b0 + h1 * b1 + h2 * b2;
-            pq[1] = h0 * w0 + h1 * w1 + h2 * w2;
-            pq[2] = h0 * x0 + h1 * x1 + h2 * x2;
-            pq[3] = h0 * y0 + h1 * y1 + h2 * y2;
-            pq[4] = h0 * z0 + h1 * z1 + h2 * z2;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {  // sum over the four lanes of the frame
-          pq[k] += __shfl_xor_sync(0xffffffffu, pq[k], 1);
-          pq[k] += __shfl_xor_sync(0xffffffffu, pq[k], 2);
-        }
-        if (n < N && j == 0) {
+          float* gAt = s_fg + n * 18;
           float gT[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-          if (mine) {
-            const float s2 = 2.0f / (qw * qw + qx * qx + qy * qy + qz * qz);
-            const float c = -s2 * s2 * pq[0];
-            gT[0] = -pq[5]; gT[1] = -pq[6]; gT[2] = pq[7];
-            gq[0] = c * qw + s2 * pq[1];
-            gq[1] = c * qx + s2 * pq[2];
-            gq[2] = c * qy + s2 * pq[3];
-            gq[3] = c * qz + s2 * pq[4];
+          if (s_mine[n]) {  // the frames this CTA's segments touch (static plan); all other slots stay zero
+            float gA[9], gR[9];
+            frame_unfold(s_A + n * 9, s_R + n * 9, kin, gAt, gAt + 9, gA, gR, k4);
+            frame_adjoint(s_pose + n * 9, s_R + n * 9, gR, gA, gT, gq);
+#pragma unroll
+            for (int k = 0; k < 18; ++k) gAt[k] = 0.f;
           }
 #pragma unroll
           for (int k = 0; k < 3; ++k) s_part[n * 7 + k] = gT[k];
@@ -798,26 +712,22 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
           for (int k = 0; k < 4; ++k) s_part[n * 7 + 3 + k] = gq[k];
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) k4[k] = warp_sum(k4[k]);  // d/d(ix, iy, kx, ky) summed over the warp's frames and columns
-        if (lane < 4) s_misc[16 + warp * 4 + lane] = (lane == 0) ? k4[0] : (lane == 1) ? k4[1] : (lane == 2) ? k4[2] : k4[3];
+        for (int k = 0; k < 4; ++k) k4[k] = warp_sum(k4[k]);  // d/d(ix, iy, kx, ky) summed over the warp's frames
+        if (lane == 0) {
+          if (N <= 32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s_misc[8 + k] = k4[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(&s_misc[8 + k], k4[k]);
+          }
+        }
       }
       __syncthreads();
       if (kProbe && pr.dbg_clock && tid == 0) ck2 = clock64();
       // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
-      float g_fx = 0.f, g_fy = 0.f;  // adjoint of the shared focal lengths: only the two threads that publish it add up the warps' shares
-      if (tid == (N * 7) % kGgsThreads || tid == (N * 7 + 1) % kGgsThreads) {
-        float kx0 = 0.f, kx1 = 0.f, kx2 = 0.f, kx3 = 0.f;
-        for (int wv = 0; wv * 32 < 4 * N; ++wv) {
-          kx0 += s_misc[16 + wv * 4 + 0];
-          kx1 += s_misc[16 + wv * 4 + 1];
-          kx2 += s_misc[16 + wv * 4 + 2];
-          kx3 += s_misc[16 + wv * 4 + 3];
-        }
-        g_fx = (-kx0 + cx * kx2) / (s_misc[12] * s_misc[12]);  // s_misc[12..13] = f'x, f'y of the current pose
-        g_fy = (-kx1 + cy * kx3) / (s_misc[13] * s_misc[13]);
-      }
       ggs_exchange<kEval>(pr.xch1, pr.xch2, P.xch_mode == 1 ? pr.acc : nullptr, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
-                          g_fx, g_fy, s_gsum, s_expect, s_mine);
+                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum, s_expect, s_mine);
       ++it_global;
       __syncthreads();
       if (kProbe && pr.dbg_clock && tid == 0) {
@@ -834,6 +744,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
         drop_phase = !kEval && (P.min_matches > 0.0) && ((double)n_valid < P.min_matches * (double)N);
         if (tid == 0) {  // the CTA-level partial sums are consumed: zero them for the next iteration (written after >= 1 barrier)
           s_misc[4] = 0.f; s_misc[5] = 0.f;
+          s_misc[8] = 0.f; s_misc[9] = 0.f; s_misc[10] = 0.f; s_misc[11] = 0.f;
           s_cta_cnt = 0;
         }
         if (drop_phase) {
@@ -861,71 +772,59 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               }
             }
           } else {
-            // The warps that hold (frame, column) threads -- 8 frames each, 3 warps at N = 20 -- finish the step REDUNDANTLY and
-            // go straight on to stage 0 of the next iteration for their own frames; everybody else waits at the one block
-            // barrier at the end.  (Three block barriers -- norm partials, updated pose, per-frame terms -- cost 1.4 + 1.1 + 1.6 k
-            // cycles for a few hundred flops.)  All reads come from the current state copy, all writes go to the next one.
-            if (warp * 32 < 4 * N) {
-              float gn2 = 0.f, pn2 = 0.f;  // clip norms over ALL elements: lane-strided, then an xor butterfly (same bits in every warp)
-              for (int e = lane; e < N9; e += 32) {
+            // clip norms: one element per thread (N9 <= 1152: up to three), warp sums, partials through shared memory
+            constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
+            float gv[kPer];
+            float gn2 = 0.f, pn2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              gv[q] = 0.f;
+              if (e < N9) {
                 const float g1 = grad_of(e);
+                gv[q] = g1;
                 gn2 = fmaf(g1, g1, gn2);
                 const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
                 pn2 = fmaf(pm, pm, pn2);
               }
+            }
+            const int warps_used = min(kGgsWarps, (N9 + 31) / 32);  // warps that hold elements (the others contribute zeros)
+            if (warp < warps_used) {
               gn2 = warp_sum(gn2);
               pn2 = warp_sum(pn2);
-              const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
-              const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
-              const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
-              const bool first = done == 0;                            // momentum buffer resets per phase
-              const int f_lo = warp * 8, f_hi = min(N, f_lo + 8);      // the frames whose state this warp writes
-              // focal lengths of ALL frames (their mean is shared), stored for the own frames only
-              float fx = 0.f, fy = 0.f;
-              for (int m = lane; m < 2 * N; m += 32) {
-                const int n = m >> 1, e = n * 9 + 7 + (m & 1);
-                const float g1 = grad_of(e) * coef;
-                const float v = first ? g1 : fmaf(P.momentum, s_vel[e], g1);
-                const float pnew = s_pose[e] - P.lr * v;
-                float fl, inr;
-                focal_of(pnew, &fl, &inr);
-                if (m & 1) fy += fl; else fx += fl;
-                if (n >= f_lo && n < f_hi) {
-                  s_vel_nxt[e] = v;
-                  s_pose_nxt[e] = pnew;
-                  s_fl_nxt[m] = fl;
-                  s_inr_nxt[m] = inr;
-                }
+              if (lane == 0) {
+                s_misc[16 + warp * 2] = gn2;
+                s_misc[16 + warp * 2 + 1] = pn2;
               }
-              fpx = warp_sum(fx) * scale_over_N;  // shared focal length = mean over frames (geometry_guided_sampling.py:142)
-              fpy = warp_sum(fy) * scale_over_N;
-              kin[0] = 1.f / fpx;
-              kin[1] = 1.f / fpy;
-              kin[2] = -cx * kin[0];
-              kin[3] = -cy * kin[1];
-              if (tid == 0) {
-                s_misc[12] = fpx;
-                s_misc[13] = fpy;
-              }
-              // translation and quaternion of the own frames
-              for (int i = lane; i < (f_hi - f_lo) * 7; i += 32) {
-                const int n = f_lo + i / 7, e = n * 9 + (i - (i / 7) * 7);
-                const float g1 = grad_of(e) * coef;
-                const float v = first ? g1 : fmaf(P.momentum, s_vel[e], g1);
-                s_vel_nxt[e] = v;
-                s_pose_nxt[e] = s_pose[e] - P.lr * v;
-              }
-              __syncwarp();
-              frame_columns(s_pose_nxt);  // stage 0 of the next iteration for the own frames
-            }
-            ++done;
-            {  // the next state becomes the current one (uniform: every thread swaps its pointers)
-              float* t0 = s_pose; s_pose = s_pose_nxt; s_pose_nxt = t0;
-              float* t1 = s_vel; s_vel = s_vel_nxt; s_vel_nxt = t1;
-              float* t2 = s_fl; s_fl = s_fl_nxt; s_fl_nxt = t2;
-              float* t3 = s_inr; s_inr = s_inr_nxt; s_inr_nxt = t3;
             }
             __syncthreads();
+            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: norm partials
+            gn2 = 0.f;
+            pn2 = 0.f;
+            for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
+              gn2 += s_misc[16 + wv * 2];
+              pn2 += s_misc[16 + wv * 2 + 1];
+            }
+            const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
+            const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
+            const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              if (e < N9) {
+                const float g1 = gv[q] * coef;
+                const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
+                s_vel[e] = v;
+                const float pnew = s_pose[e] - P.lr * v;
+                s_pose[e] = pnew;
+                const int n = e / 9, c = e - n * 9;
+                if (c >= 7) focal_of(pnew, &s_fl[n * 2 + (c - 7)], &s_inr[n * 2 + (c - 7)]);
+              }
+            }
+            ++done;
+            __syncthreads();
+            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[7] += c - ck3; ck3 = c; }  // probe: coefficient + update
+            frames_forward();  // stage 0 of the next iteration (one block barrier inside)
           }
         }
       }

@@ -21,9 +21,9 @@ clk = ctx.ggs_clocks(True, read=True)
 used = clk[clk[:, 5] > 0]
 it = used[0, 5]
 print(f"launch {e0.elapsed_time(e1):.3f} ms, {it} iterations, {len(used)} CTAs, {e0.elapsed_time(e1)*1e3/it:.2f} us/iter")
-names = ['-', 'stage1', 'stage2b', 'exchange', 'stage2a', 'iters', 'step+stage0', '-']
+names = ['stage3 norms', 'stage1', 'stage2b', 'exchange', 'stage2a', 'iters', 'next stage0', 'stage3 update']
 for k, n in enumerate(names):
-    if k in (0, 5, 7): continue
+    if k == 5: continue
     per = used[:, k] / it
     print(f"{n:10s} cycles/iter: mean {per.mean():8.0f}  min {per.min():8.0f}  max {per.max():8.0f}")
 print("total cycles/iter (cta0):", (used[0, :5].sum() + used[0, 6] + used[0, 7]) / it)
