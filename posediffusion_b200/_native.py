@@ -6,6 +6,7 @@ missing, or no sm_100 GPU is present, every compute call raises.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import os
 import threading
 from typing import Dict, List, Optional, Sequence
@@ -140,6 +141,15 @@ def vit_pos_table(pos_embed: np.ndarray, grid_h: int, grid_w: int) -> np.ndarray
     if rc != 0:
         raise NativeError(f"pdb_vit_pos_table failed ({rc})")
     return out
+
+
+_module_tokens = itertools.count(1)
+
+
+def module_token() -> int:
+    """Process-unique, never reused identity of a module for the device-side weight caches (`id()` of a freed module can come
+    back for a new one whose parameters land in the same allocator blocks with the same versions)."""
+    return next(_module_tokens)
 
 
 GGS_LAYOUTS = {"plain": 0, "paired": 1}

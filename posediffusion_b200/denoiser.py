@@ -75,7 +75,8 @@ class Denoiser(nn.Module):
             nn.Linear(arch["d_model"], mlp_hidden_dim), nn.LayerNorm(mlp_hidden_dim), nn.ReLU(inplace=True),
             nn.Linear(mlp_hidden_dim, target_dim),
         )
-        self._native_key = None
+        self._native_token = _native.module_token()  # identity for the context's weight cache (never reused, unlike id())
+        self._native_epoch = 0
 
     # ---- native weight sync -------------------------------------------------------------------------
     def ordered_parameters(self) -> List[torch.Tensor]:
@@ -89,11 +90,15 @@ class Denoiser(nn.Module):
         if device.type != "cuda":
             raise _native.NativeError("Denoiser parameters are on the CPU: call .to('cuda') (no CPU fallback)")
         ctx = _native.Context.get(device)
-        key = (id(self), tuple((p.data_ptr(), p._version) for p in params))
+        key = (self._native_token, self._native_epoch, tuple((p.data_ptr(), p._version) for p in params))
         if ctx.weights_key != key:
             ctx.load_denoiser(params)
             ctx.weights_key = key
         return ctx
+
+    def invalidate_native_weights(self) -> None:
+        """Force a re-upload at the next call (needed after editing parameters through `.data`, which does not bump `_version`)."""
+        self._native_epoch += 1
 
     def forward(self, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
         """x [B,N,9], t [B] (all entries equal, as the sampler passes them), z [B,N,384] -> eps [B,N,9]."""

@@ -87,7 +87,9 @@ class MultiScaleImageFeatureExtractor(nn.Module):
 
     def _sync_weights(self, ctx: "_native.Context"):
         params = list(self._net.state_dict().values())
-        key = (id(self),) + tuple((p.data_ptr(), p._version) for p in params)
+        if not hasattr(self, "_native_token"):
+            self._native_token = _native.module_token()  # never reused, unlike id()
+        key = (self._native_token,) + tuple((p.data_ptr(), p._version) for p in params)
         if getattr(ctx, "vit_key", None) != key:  # the context holds ONE backbone: reload if another module used it since
             ctx.load_vit(params)
             ctx.vit_key = key

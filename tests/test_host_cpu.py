@@ -254,3 +254,20 @@ def test_match_cache_is_keyed_on_content_not_only_identity():
         ggs_mod.packed_matches(ctx, dict(d, kp1=np.full((10, 2), float(i))))
     assert len(ggs_mod._KEEP) <= ggs_mod._KEEP_MAX
     ggs_mod.invalidate_matches()
+
+
+def test_weight_cache_identity_is_never_reused():
+    """the context's weight cache was keyed on id(module); a freed module's id (and allocator blocks, and parameter
+    versions) can come back for a NEW module, which then ran with the old weights (seen once as a 9 % mismatch in a GPU test).
+    The key now carries a process-unique token and an explicit invalidation epoch."""
+    cfg = dict(d_model=512, nhead=4, dim_feedforward=1024, num_encoder_layers=8, dropout=0.1, batch_first=True, norm_first=True)
+    tokens = set()
+    for _ in range(3):
+        m = pdb.Denoiser(TRANSFORMER=cfg)
+        tokens.add(m._native_token)
+        del m
+    assert len(tokens) == 3
+    m = pdb.Denoiser(TRANSFORMER=cfg)
+    e0 = m._native_epoch
+    m.invalidate_native_weights()
+    assert m._native_epoch == e0 + 1
