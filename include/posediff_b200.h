@@ -18,6 +18,8 @@
  *   pdb_sample_loop        <- GaussianDiffusion.sample / p_sample_loop   (models/gaussian_diffuser.py:285-306)
  *   pdb_sample_loop_host   <- the same call with HOST buffers (demo.py:108 as a user sees it: features and
  *                             matches on the host, poses back on the host)
+ *   pdb_sample_loop_host_matches <- the same call starting from the reference's matches_dict arrays (demo.py:94-108:
+ *                             extract_match output straight into the sampler); packing overlaps the unguided steps
  *
  * Conventions: plain pointers and sizes only (no torch types).  `*_dev` pointers are CUDA device pointers
  * on the context's device, `*_host` are host pointers, `stream` is a cudaStream_t passed as void*
@@ -97,6 +99,12 @@ int pdb_debug_ggs_clocks(pdb_context* ctx, int32_t enable, int64_t* out, int32_t
 /* Swap-AB tcgen05 tiles (weights on the 128-row UMMA M side, 32 / 64 / 96 tokens on the N side) for GEMMs with at most 96 tokens
  * and O % 128 == 0; default off (measured slower than 128-token tiles without split-K).  Debug / measurement switch. */
 int pdb_debug_tc_swap(pdb_context* ctx, int32_t on);
+
+/* Stage hand-over inside the persistent fp32 denoiser kernel: 0 (default) = plain floats and a group barrier per stage; 1 = every
+ * activation travels as a 64-bit {fp32, version tag} word and consumers poll the data itself, no barrier between the 43 stages of
+ * a diffusion step.  Same arithmetic, bit-identical results; the flagged variant is ~3x slower (148 CTAs polling 80 KB tiles
+ * saturate L2).  Debug / measurement switch (environment: PDB_DEN_FLAG). */
+int pdb_debug_denoiser_handover(pdb_context* ctx, int32_t flagged);
 
 /* Denoiser engine: 0 = auto (exact-fp32 persistent kernel below 128 tokens per GPU, tcgen05/TMA tensor-core tiles with TF32
  * products at or above), 1 = always fp32, 2 = always tensor cores. */
@@ -199,6 +207,17 @@ int pdb_sample_loop_host(pdb_context* ctx, const float* z_host, const float* dra
                          int32_t frames, pdb_matches* const* problems, int32_t n_problems, const pdb_ggs_config* cfg,
                          int32_t cond_start_step, float* pose_host, float* trail_host, pdb_ggs_stats* stats_host,
                          void* stream);
+
+/* The end-to-end call that starts from the reference's match format: kp1[b] / kp2[b] (float64 [m_total[b], 2]) and i12[b]
+ * (int64 [m_total[b], 2]) are the HOST arrays of sequence b's matches_dict (util/match_extraction.py:50-77), as pdb_matches_pack
+ * takes them.  The sets are packed and uploaded while the unguided steps t = T-1 .. cond_start_step already run on the GPU, then
+ * the guided steps follow; the packed sets are released before the call returns.  Results are those of pdb_matches_pack +
+ * pdb_sample_loop_host.  cfg must not be NULL. */
+int pdb_sample_loop_host_matches(pdb_context* ctx, const float* z_host, const float* draws_host, int32_t batch, int32_t frames,
+                                 const double* const* kp1, const double* const* kp2, const int64_t* const* i12,
+                                 const int64_t* m_total, int32_t height, int32_t width, const pdb_ggs_config* cfg,
+                                 int32_t cond_start_step, float* pose_host, float* trail_host, pdb_ggs_stats* stats_host,
+                                 void* stream);
 
 /* ---- image features (widened row) ---------------------------------------------------
  * z = MultiScaleImageFeatureExtractor(image) (models/image_feature_extractor.py:27-87): the DINO ViT-S/16 backbone that the

@@ -80,6 +80,7 @@ EXPORTS = {
     "pdb_matches_free": (None, [C.c_void_p]),
     "pdb_matches_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "pdb_debug_tc_swap": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pdb_debug_denoiser_handover": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_ggs_layout": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdb_ggs_layout_get": (C.c_int, [C.c_void_p]),
     "pdb_debug_pack_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
@@ -96,6 +97,7 @@ EXPORTS = {
     "pdb_extract_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pdb_extract_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p]),
     "pdb_sample_loop_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdb_sample_loop_host_matches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(GgsConfig), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -278,6 +280,10 @@ class Context:
     def set_denoiser_engine(self, mode: str = "auto"):
         """'auto' (fp32 kernel below 128 tokens, tensor cores above), 'fp32' or 'tf32'."""
         self._ok(self.lib.pdb_denoiser_engine(self.handle, {"auto": 0, "fp32": 1, "tf32": 2}[mode]), "pdb_denoiser_engine")
+
+    def set_denoiser_handover(self, flagged: bool):
+        """Stage hand-over of the persistent fp32 denoiser kernel: group barriers (default) or flag-carrying words."""
+        self._ok(self.lib.pdb_debug_denoiser_handover(self.handle, int(flagged)), "pdb_debug_denoiser_handover")
 
     def set_tc_swap(self, on: bool):
         """Swap-AB tcgen05 tiles for GEMMs with at most 96 tokens (default off; see profiles/r2_bench_tc_small.json)."""
@@ -520,6 +526,41 @@ class Context:
                                                    pose_out.ctypes.data, trail_out.ctypes.data if trail_out is not None else None,
                                                    stats_out.ctypes.data if stats_out is not None else None,
                                                    _stream_ptr(self.device)), "pdb_sample_loop_host")
+        return pose_out
+
+    def sample_loop_host_matches(self, z: np.ndarray, draws: np.ndarray, matches_dicts, cfg, cond_start_step: int,
+                                 pose_out: np.ndarray, trail_out: Optional[np.ndarray] = None, stats_out: Optional[np.ndarray] = None):
+        """The end-to-end call from the reference's matches_dict format (one dict per sequence): the match sets are packed and
+        uploaded while the unguided steps already run (pdb_sample_loop_host_matches)."""
+        B, N, _ = z.shape
+        if len(matches_dicts) != B:
+            raise ValueError(f"{len(matches_dicts)} match sets for a batch of {B} sequences (one per sequence)")
+        keep, shape = [], None
+        for md in matches_dicts:
+            frames, _, height, width = (int(v) for v in md["img_shape"])
+            if frames != N:
+                raise ValueError(f"match set of {frames} frames used with {N} frames")
+            if shape is not None and shape != (height, width):
+                raise ValueError("all sequences of one call must share the image size")
+            shape = (height, width)
+            kp1 = np.ascontiguousarray(md["kp1"], dtype=np.float64).reshape(-1, 2)
+            kp2 = np.ascontiguousarray(md["kp2"], dtype=np.float64).reshape(-1, 2)
+            i12 = np.ascontiguousarray(md["i12"], dtype=np.int64).reshape(-1, 2)
+            if not (len(kp1) == len(kp2) == len(i12)):
+                raise ValueError("kp1, kp2 and i12 must have the same number of rows")
+            keep.append((kp1, kp2, i12))
+        ptrs = [(C.c_void_p * B)(*[k[j].ctypes.data for k in keep]) for j in range(3)]
+        counts = (C.c_int64 * B)(*[len(k[0]) for k in keep])
+        conf = ggs_config_struct(cfg)
+        with torch.cuda.device(self.device):
+            rc = self.lib.pdb_sample_loop_host_matches(self.handle, z.ctypes.data, draws.ctypes.data, B, N, ptrs[0], ptrs[1], ptrs[2],
+                                                       counts, shape[0], shape[1], C.byref(conf), int(cond_start_step),
+                                                       pose_out.ctypes.data, trail_out.ctypes.data if trail_out is not None else None,
+                                                       stats_out.ctypes.data if stats_out is not None else None,
+                                                       _stream_ptr(self.device))
+        if rc == -1:
+            raise ValueError(self.lib.pdb_last_error(self.handle).decode())
+        self._ok(rc, "pdb_sample_loop_host_matches")
         return pose_out
 
 

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "context.cuh"
 #include "denoiser.cuh"
@@ -102,13 +103,13 @@ int pick_token_tile(int tokens) {
   return best;
 }
 
-template <int TS>
+template <int TS, bool kFlag>
 int launch_denoiser(Context* ctx, const DenoiserRun& run, int grid, cudaStream_t st) {
   const size_t smem = denoiser_smem_bytes(TS, run.frames);
   if (smem > ctx->smem_optin) return ctx->fail(PDB_ERR_LIMIT, "denoiser needs %zu B shared memory", smem);
-  size_t& attr_bytes = ctx->attr_den[TS / 4 - 1];  // static shared memory counts against the opt-in limit: ask for what we use
+  size_t& attr_bytes = ctx->attr_den[(kFlag ? 8 : 0) + TS / 4 - 1];  // static shared memory counts against the opt-in limit: ask for what we use
   if (smem > attr_bytes) {
-    PDB_CUDA(ctx, cudaFuncSetAttribute(denoiser_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDB_CUDA(ctx, cudaFuncSetAttribute(denoiser_kernel<TS, kFlag>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
   cudaLaunchConfig_t cfg = {};
@@ -123,7 +124,7 @@ int launch_denoiser(Context* ctx, const DenoiserRun& run, int grid, cudaStream_t
   cfg.numAttrs = 1;
   {
     ScopedTimer timer(ctx, st, 1);
-    PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, denoiser_kernel<TS>, ctx->weights->dev, run));
+    PDB_CUDA(ctx, cudaLaunchKernelEx(&cfg, denoiser_kernel<TS, kFlag>, ctx->weights->dev, run));
   }
   ctx->launches += 1;
   return PDB_OK;
@@ -153,6 +154,28 @@ int enqueue_denoiser(Context* ctx, DenoiserRun run, cudaStream_t st) {
   run.ff = ws;    ws += (size_t)S * kFF;
   run.u = ws;
   PDB_CUDA(ctx, cudaMemsetAsync(run.bar, 0, 256, st));
+  // stage hand-over: group barriers, or flag-carrying activation words (no barriers) when pdb_debug_denoiser_handover /
+  // PDB_DEN_FLAG=1 selects that instantiation (measured slower, kept as a tested alternative)
+  const bool flagged = ctx->den_flag != 0;
+  if (flagged) {
+    const size_t words = denoiser_flag_ws_words(S);
+    const unsigned tags = (unsigned)(run.t_hi - run.t_lo + 1) * kTagsPerStep;
+    const bool fresh = ctx->den_flag_ws_bytes < sizeof(unsigned long long) * words;
+    if (int rc = ensure_buffer(ctx, &ctx->den_flag_ws, &ctx->den_flag_ws_bytes, sizeof(unsigned long long) * words)) return rc;
+    if (fresh || ctx->den_tag > 0xffffffffu - tags - 1u) {  // new buffer, or the 32-bit versions would wrap: start over from tag 1
+      PDB_CUDA(ctx, cudaMemsetAsync(ctx->den_flag_ws, 0, ctx->den_flag_ws_bytes, st));
+      ctx->den_tag = 1u;
+    }
+    unsigned long long* fw = static_cast<unsigned long long*>(ctx->den_flag_ws);
+    run.fh = fw;   fw += (size_t)S * kDM;
+    run.fqkv = fw; fw += (size_t)S * 2 * 3 * kDM;
+    run.fatt = fw; fw += (size_t)S * kDM;
+    run.fff = fw;  fw += (size_t)S * kFF;
+    run.fu = fw;   fw += (size_t)S * kHid;
+    run.fx = fw;
+    run.tag_base = ctx->den_tag;
+    ctx->den_tag += tags;
+  }
   run.dbg_clock = ctx->den_clock ? ctx->ggs_clock : nullptr;  // pdb_debug_ggs_clocks(enable = 2): probe the denoiser instead
   const int TS = pick_token_tile(S);
   const int tiles = (S + TS - 1) / TS;
@@ -162,13 +185,75 @@ int enqueue_denoiser(Context* ctx, DenoiserRun run, cudaStream_t st) {
     const int v = atoi(g);
     if (v >= 1 && v < grid) grid = v;
   }
-  switch (TS) {
-    case 8: return launch_denoiser<8>(ctx, run, grid, st);
-    case 16: return launch_denoiser<16>(ctx, run, grid, st);
-    case 20: return launch_denoiser<20>(ctx, run, grid, st);
-    case 24: return launch_denoiser<24>(ctx, run, grid, st);
-    default: return launch_denoiser<32>(ctx, run, grid, st);
+  if (flagged) {
+    switch (TS) {
+      case 8: return launch_denoiser<8, true>(ctx, run, grid, st);
+      case 16: return launch_denoiser<16, true>(ctx, run, grid, st);
+      case 20: return launch_denoiser<20, true>(ctx, run, grid, st);
+      case 24: return launch_denoiser<24, true>(ctx, run, grid, st);
+      default: return launch_denoiser<32, true>(ctx, run, grid, st);
+    }
   }
+  switch (TS) {
+    case 8: return launch_denoiser<8, false>(ctx, run, grid, st);
+    case 16: return launch_denoiser<16, false>(ctx, run, grid, st);
+    case 20: return launch_denoiser<20, false>(ctx, run, grid, st);
+    case 24: return launch_denoiser<24, false>(ctx, run, grid, st);
+    default: return launch_denoiser<32, false>(ctx, run, grid, st);
+  }
+}
+
+// The sampling loop in two halves, so that a caller can do host work (match packing) between them while the first half runs:
+// loop_prefix enqueues x_T = draws[0] (gaussian_diffuser.py:289) and the unguided steps t = T-1 .. guide_below in ONE launch,
+// loop_guided the guided steps (denoiser -> posterior mean -> GGS in place).
+struct LoopState {
+  DenoiserRun run = {};
+  int guide_below = 0;
+  bool first = true;
+  size_t n = 0;
+  float* pose = nullptr;
+  float* trail = nullptr;
+};
+
+int loop_prefix(Context* ctx, const float* z_dev, const float* draws_dev, int batch, int frames, int guide_below, float* pose_dev,
+                float* trail_dev, cudaStream_t st, LoopState* loop) {
+  if (guide_below > kT) guide_below = kT;
+  if (guide_below < 0) guide_below = 0;
+  const size_t n = (size_t)batch * frames * kTargetDim;
+  PDB_CUDA(ctx, cudaMemcpyAsync(pose_dev, draws_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (trail_dev) PDB_CUDA(ctx, cudaMemcpyAsync(trail_dev, draws_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  loop->n = n;
+  loop->guide_below = guide_below;
+  loop->pose = pose_dev;
+  loop->trail = trail_dev;
+  DenoiserRun& run = loop->run;
+  run.batch = batch; run.frames = frames;
+  run.guide_below = guide_below;
+  run.x = pose_dev; run.z = z_dev; run.draws = draws_dev; run.trail = trail_dev;
+  if (guide_below < kT) {
+    run.t_hi = kT - 1; run.t_lo = guide_below;
+    run.compute_zproj = 1;
+    if (int rc = enqueue_denoiser(ctx, run, st)) return rc;
+    loop->first = false;
+  }
+  return PDB_OK;
+}
+
+int loop_guided(Context* ctx, LoopState* loop, pdb_matches* const* problems, const pdb_ggs_config* cfg, pdb_ggs_stats* stats_dev,
+                cudaStream_t st) {
+  DenoiserRun& run = loop->run;
+  for (int t = loop->guide_below - 1; t >= 0; --t) {
+    run.t_hi = run.t_lo = t;
+    run.compute_zproj = loop->first ? 1 : 0;
+    loop->first = false;
+    if (int rc = enqueue_denoiser(ctx, run, st)) return rc;
+    pdb_ggs_stats* stats = stats_dev ? stats_dev + (size_t)(loop->guide_below - 1 - t) * run.batch : nullptr;
+    if (int rc = enqueue_ggs(ctx, problems, run.batch, run.frames, loop->pose, cfg, stats, st)) return rc;
+    if (loop->trail)
+      PDB_CUDA(ctx, cudaMemcpyAsync(loop->trail + (size_t)(kT - t) * loop->n, loop->pose, sizeof(float) * loop->n,
+                                    cudaMemcpyDeviceToDevice, st));
+  }
+  return PDB_OK;
 }
 
 }  // namespace
@@ -188,9 +273,11 @@ void pdb_destroy(pdb_context* c) {
   vit_release(ctx);
   if (ctx->ggs_ws) cudaFree(ctx->ggs_ws);
   if (ctx->den_ws) cudaFree(ctx->den_ws);
+  if (ctx->den_flag_ws) cudaFree(ctx->den_flag_ws);
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->tc_graph) cudaGraphExecDestroy(ctx->tc_graph);
   if (ctx->tc_capture_stream) cudaStreamDestroy(ctx->tc_capture_stream);
+  if (ctx->pack_stream) cudaStreamDestroy(ctx->pack_stream);
   for (auto& b : ctx->pool) cudaFree(b.first);
   if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->ggs_clock) cudaFree(ctx->ggs_clock);
@@ -456,35 +543,9 @@ int pdb_sample_loop(pdb_context* c, const float* z_dev, const float* draws_dev, 
     if (int rc = check_ggs_problems(ctx, problems, batch, frames)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t n = (size_t)batch * frames * kTargetDim;
-  int guide_below = problems ? cond_start_step : 0;
-  if (guide_below > kT) guide_below = kT;
-  if (guide_below < 0) guide_below = 0;
-  // x_T = draws[0]  (gaussian_diffuser.py:289)
-  PDB_CUDA(ctx, cudaMemcpyAsync(pose_dev, draws_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-  if (trail_dev) PDB_CUDA(ctx, cudaMemcpyAsync(trail_dev, draws_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-  DenoiserRun run = {};
-  run.batch = batch; run.frames = frames;
-  run.guide_below = guide_below;
-  run.x = pose_dev; run.z = z_dev; run.draws = draws_dev; run.trail = trail_dev;
-  bool first = true;
-  if (guide_below < kT) {  // unguided prefix t = T-1 .. guide_below in ONE launch
-    run.t_hi = kT - 1; run.t_lo = guide_below;
-    run.compute_zproj = 1;
-    if (int rc = enqueue_denoiser(ctx, run, st)) return rc;
-    first = false;
-  }
-  for (int t = guide_below - 1; t >= 0; --t) {  // guided steps: denoiser -> posterior mean -> GGS in place
-    run.t_hi = run.t_lo = t;
-    run.compute_zproj = first ? 1 : 0;
-    first = false;
-    if (int rc = enqueue_denoiser(ctx, run, st)) return rc;
-    pdb_ggs_stats* stats = stats_dev ? stats_dev + (size_t)(guide_below - 1 - t) * batch : nullptr;
-    if (int rc = enqueue_ggs(ctx, problems, batch, frames, pose_dev, cfg, stats, st)) return rc;
-    if (trail_dev)
-      PDB_CUDA(ctx, cudaMemcpyAsync(trail_dev + (size_t)(kT - t) * n, pose_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-  }
-  return PDB_OK;
+  LoopState loop;
+  if (int rc = loop_prefix(ctx, z_dev, draws_dev, batch, frames, problems ? cond_start_step : 0, pose_dev, trail_dev, st, &loop)) return rc;
+  return loop_guided(ctx, &loop, problems, cfg, stats_dev, st);
 }
 
 int pdb_sample_loop_host(pdb_context* c, const float* z_host, const float* draws_host, int32_t batch, int32_t frames,
@@ -519,6 +580,60 @@ int pdb_sample_loop_host(pdb_context* c, const float* z_host, const float* draws
   if (trail_host) PDB_CUDA(ctx, cudaMemcpyAsync(trail_host, trail_dev, sizeof(float) * f_trail, cudaMemcpyDeviceToHost, st));
   if (stats_host && stats_bytes) PDB_CUDA(ctx, cudaMemcpyAsync(stats_host, stats_dev, stats_bytes, cudaMemcpyDeviceToHost, st));
   PDB_CUDA(ctx, cudaStreamSynchronize(st));
+  return PDB_OK;
+}
+
+// The end-to-end call of a guided run that starts from the reference's match format (host arrays, one match set per sequence):
+// the match sets are packed and uploaded WHILE the unguided prefix of the loop (t = T-1 .. cond_start_step, one launch) runs on
+// the GPU -- the packer is host work plus a copy on its own stream, the prefix does not need the matches.
+int pdb_sample_loop_host_matches(pdb_context* c, const float* z_host, const float* draws_host, int32_t batch, int32_t frames,
+                                 const double* const* kp1, const double* const* kp2, const int64_t* const* i12,
+                                 const int64_t* m_total, int32_t height, int32_t width, const pdb_ggs_config* cfg,
+                                 int32_t cond_start_step, float* pose_host, float* trail_host, pdb_ggs_stats* stats_host,
+                                 void* stream) {
+  if (!c) return PDB_ERR_INVALID;
+  Context* ctx = reinterpret_cast<Context*>(c);
+  if (!z_host || !draws_host || !pose_host || !kp1 || !kp2 || !i12 || !m_total || !cfg)
+    return ctx->fail(PDB_ERR_INVALID, "null argument");
+  if (batch < 1 || frames < 1) return ctx->fail(PDB_ERR_INVALID, "bad batch / frames");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->pack_stream) PDB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pack_stream, cudaStreamNonBlocking));
+  const size_t S = (size_t)batch * frames, n = S * kTargetDim;
+  const int guided = cond_start_step < 0 ? 0 : (cond_start_step > kT ? kT : cond_start_step);
+  const size_t f_z = S * kZ, f_draws = (size_t)(kT + 1) * n, f_pose = n, f_trail = trail_host ? (size_t)(kT + 1) * n : 0;
+  const size_t stats_bytes = stats_host ? sizeof(pdb_ggs_stats) * (size_t)guided * batch : 0;
+  const size_t bytes = sizeof(float) * (f_z + f_draws + f_pose + f_trail) + stats_bytes + 256;
+  if (int rc = ensure_buffer(ctx, &ctx->stage, &ctx->stage_bytes, bytes)) return rc;
+  float* z_dev = static_cast<float*>(ctx->stage);
+  float* draws_dev = z_dev + f_z;
+  float* pose_dev = draws_dev + f_draws;
+  float* trail_dev = trail_host ? pose_dev + f_pose : nullptr;
+  pdb_ggs_stats* stats_dev = stats_host ? reinterpret_cast<pdb_ggs_stats*>(pose_dev + f_pose + f_trail) : nullptr;
+  PDB_CUDA(ctx, cudaMemcpyAsync(z_dev, z_host, sizeof(float) * f_z, cudaMemcpyHostToDevice, st));
+  PDB_CUDA(ctx, cudaMemcpyAsync(draws_dev, draws_host, sizeof(float) * f_draws, cudaMemcpyHostToDevice, st));
+  if (stats_dev) PDB_CUDA(ctx, cudaMemsetAsync(stats_dev, 0, stats_bytes, st));
+  LoopState loop;
+  if (int rc = loop_prefix(ctx, z_dev, draws_dev, batch, frames, guided, pose_dev, trail_dev, st, &loop)) return rc;
+  // ---- host: pack while the prefix runs (pdb_matches_pack returns once ITS stream has taken the upload) ----
+  std::vector<pdb_matches*> sets((size_t)batch, nullptr);
+  int rc = PDB_OK;
+  for (int b = 0; b < batch && rc == PDB_OK; ++b)
+    rc = pdb_matches_pack(c, kp1[b], kp2[b], i12[b], m_total[b], frames, height, width, 0, ctx->pack_stream, &sets[b]);
+  if (rc == PDB_OK) rc = check_ggs_problems(ctx, sets.data(), batch, frames);
+  if (rc == PDB_OK) rc = loop_guided(ctx, &loop, sets.data(), cfg, stats_dev, st);
+  cudaError_t err = cudaSuccess;
+  if (rc == PDB_OK) {
+    err = cudaMemcpyAsync(pose_host, pose_dev, sizeof(float) * f_pose, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess && trail_host) err = cudaMemcpyAsync(trail_host, trail_dev, sizeof(float) * f_trail, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess && stats_host && stats_bytes)
+      err = cudaMemcpyAsync(stats_host, stats_dev, stats_bytes, cudaMemcpyDeviceToHost, st);
+  }
+  const cudaError_t sync = cudaStreamSynchronize(st);  // also on the error path: the match sets are released below
+  for (pdb_matches* m : sets) pdb_matches_free(m);
+  if (rc != PDB_OK) return rc;
+  if (err != cudaSuccess || sync != cudaSuccess)
+    return ctx->fail(PDB_ERR_CUDA, "sample loop failed: %s", cudaGetErrorString(err != cudaSuccess ? err : sync));
   return PDB_OK;
 }
 

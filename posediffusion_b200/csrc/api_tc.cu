@@ -191,13 +191,13 @@ __global__ void __launch_bounds__(kDenThreads) attention_kernel(const float* __r
   extern __shared__ __align__(16) float att_smem[];
   const int chunks = (frames + kDenWarps - 1) / kDenWarps;
   const int item = blockIdx.x;
-  attention_item(att_smem, qkv, att, item / (kHeads * chunks), (item / chunks) % kHeads, item % chunks, frames);
+  attention_item<false>(att_smem, qkv, att, item / (kHeads * chunks), (item / chunks) % kHeads, item % chunks, frames, 0u, 0u);
 }
 // the timestep lives on the device (tstate = {t, t_lo}) so that one captured graph serves every diffusion step
 __global__ void __launch_bounds__(kDenThreads) tail_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R, const int* __restrict__ tstate) {
   const int s = blockIdx.x * kDenWarps + (threadIdx.x >> 5);
   const int t = tstate[0];
-  if (s < R.tokens) tail_token(W, R, s, t, t == tstate[1]);
+  if (s < R.tokens) tail_token<false>(W, R, s, t, t == tstate[1], 0u, 0u);
 }
 __global__ void step_set_kernel(int* tstate, int t, int t_lo) { tstate[0] = t; tstate[1] = t_lo; }
 __global__ void step_dec_kernel(int* tstate) { tstate[0] -= 1; }
@@ -318,5 +318,11 @@ extern "C" int pdb_debug_tc_swap(pdb_context* c, int32_t on) {
 extern "C" int pdb_denoiser_engine(pdb_context* c, int32_t mode) {
   if (!c || mode < 0 || mode > 2) return PDB_ERR_INVALID;
   reinterpret_cast<Context*>(c)->denoiser_engine = mode;
+  return PDB_OK;
+}
+
+extern "C" int pdb_debug_denoiser_handover(pdb_context* c, int32_t flagged) {
+  if (!c) return PDB_ERR_INVALID;
+  reinterpret_cast<Context*>(c)->den_flag = flagged != 0;
   return PDB_OK;
 }

@@ -82,6 +82,14 @@ inline void st_ll(unsigned long long* p, unsigned bits, unsigned tag) {
   __atomic_store_n(p, ((unsigned long long)tag << 32) | (unsigned long long)bits, __ATOMIC_RELAXED);
 }
 inline unsigned long long ld_ll(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void ld_ll2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  a = __atomic_load_n(p, __ATOMIC_RELAXED);
+  b = __atomic_load_n(p + 1, __ATOMIC_RELAXED);
+}
+inline void st_ll2(unsigned long long* p, unsigned bits0, unsigned bits1, unsigned tag) {
+  st_ll(p, bits0, tag);
+  st_ll(p + 1, bits1, tag);
+}
 // {fp32 sum, fp32 arrivals} accumulators of the one-hop all-reduce: the pair is updated / read as ONE 64-bit unit here
 inline void red_pair_add(float* p, float v) {
   unsigned long long* u = reinterpret_cast<unsigned long long*>(p);
@@ -148,6 +156,15 @@ __device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p)
   unsigned long long w;
   asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return w;
+}
+// two neighbouring words with one 16-byte access (16-byte aligned); each 64-bit element is single-copy atomic on its own
+__device__ __forceinline__ void ld_ll2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_ll2(unsigned long long* p, unsigned bits0, unsigned bits1, unsigned tag) {
+  const unsigned long long w0 = ((unsigned long long)tag << 32) | (unsigned long long)bits0;
+  const unsigned long long w1 = ((unsigned long long)tag << 32) | (unsigned long long)bits1;
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1,%2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
 __device__ __forceinline__ void ll_backoff() {}
 // One-hop all-reduce accumulators: {fp32 sum, fp32 arrivals} in one 8-byte word.  ONE vector reduction adds {v, 1.0} to the

@@ -28,6 +28,13 @@ struct Context {
   DenoiserWeights* weights = nullptr;
   void* den_ws = nullptr;
   size_t den_ws_bytes = 0;
+  // stage hand-over of the persistent denoiser kernel: 0 = group barriers (default), 1 = flag-carrying activation words, no
+  // barriers (pdb_debug_denoiser_handover / PDB_DEN_FLAG; parity-identical but 3x slower: 148 CTAs polling an 80 KB tile saturate
+  // L2, profiles/r2_negative_den_flagged_*.txt)
+  int den_flag = 0;
+  void* den_flag_ws = nullptr;
+  size_t den_flag_ws_bytes = 0;
+  unsigned den_tag = 1;  // next unused version tag (0 = never written)
   // stage timing probe of the GGS kernel (debug): [ctas][8] cycle sums
   long long* ggs_clock = nullptr;
   int ggs_clock_ctas = 0;
@@ -36,9 +43,10 @@ struct Context {
   cudaGraphExec_t tc_graph = nullptr;
   std::vector<size_t> tc_graph_key;
   cudaStream_t tc_capture_stream = nullptr;
+  cudaStream_t pack_stream = nullptr;  // match uploads of pdb_sample_loop_host_matches (overlap the unguided prefix)
   int tc_graph_nodes = 0;
   // cudaFuncSetAttribute is per device: remember per context (= per device) what was already requested
-  size_t attr_ggs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_den[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
+  size_t attr_ggs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_den[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
   bool attr_tc = false, attr_tc128 = false;
   bool tc_swap = false;     // swap-AB tcgen05 tiles for <= 96 tokens (pdb_debug_tc_swap); default off, see profiles/r2_bench_tc_small.json
   bool attr_tc_swap[3] = {false, false, false};  // swap-AB instantiations (32 / 64 / 96 tokens on the N side)

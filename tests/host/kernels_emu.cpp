@@ -198,8 +198,9 @@ std::vector<float> naive_linear(const float* X, int S, int K, const float* W, in
   return Y;
 }
 template <int TS>
-void run_denoiser(const pdb::DenoiserDev& W, const pdb::DenoiserRun& R, int grid) {
-  emu::launch(grid, pdb::kDenThreads, [&]() { pdb::denoiser_kernel<TS>(W, R); });
+void run_denoiser(const pdb::DenoiserDev& W, const pdb::DenoiserRun& R, int grid, bool flagged) {
+  if (flagged) emu::launch(grid, pdb::kDenThreads, [&]() { pdb::denoiser_kernel<TS, true>(W, R); });
+  else emu::launch(grid, pdb::kDenThreads, [&]() { pdb::denoiser_kernel<TS, false>(W, R); });
 }
 }  // namespace
 
@@ -269,13 +270,29 @@ extern "C" int denoiser_emu_run(const float* const* tensors, const float* sched 
   R.att = p;   p += (size_t)S * kDM;
   R.ff = p;    p += (size_t)S * kFF;
   R.u = p;
+  // stage hand-over as enqueue_denoiser selects it: flag-carrying words when PDB_DEN_FLAG=1.  The buffers start out holding
+  // stale words of an "earlier launch" (tags below tag_base, garbage values) so that a reader that accepts a wrong version fails.
+  const bool flagged = getenv("PDB_DEN_FLAG") && atoi(getenv("PDB_DEN_FLAG")) != 0;
+  std::vector<unsigned long long> fws(denoiser_flag_ws_words(S) + 16);
+  const unsigned tag_base = 1000u;
+  for (size_t i = 0; i < fws.size(); ++i) fws[i] = ((unsigned long long)(tag_base - 1u - (unsigned)(i % 7)) << 32) | 0x7fc00000ull;  // NaN payloads
+  {
+    unsigned long long* fw = fws.data();
+    R.fh = fw;   fw += (size_t)S * kDM;
+    R.fqkv = fw; fw += (size_t)S * 2 * 3 * kDM;
+    R.fatt = fw; fw += (size_t)S * kDM;
+    R.fff = fw;  fw += (size_t)S * kFF;
+    R.fu = fw;   fw += (size_t)S * kHid;
+    R.fx = fw;
+    R.tag_base = tag_base;
+  }
   if (denoiser_smem_bytes(token_tile, frames) > emu::kSharedBytes) return -2;
   switch (token_tile) {
-    case 8: run_denoiser<8>(D, R, grid); break;
-    case 16: run_denoiser<16>(D, R, grid); break;
-    case 20: run_denoiser<20>(D, R, grid); break;
-    case 24: run_denoiser<24>(D, R, grid); break;
-    case 32: run_denoiser<32>(D, R, grid); break;
+    case 8: run_denoiser<8>(D, R, grid, flagged); break;
+    case 16: run_denoiser<16>(D, R, grid, flagged); break;
+    case 20: run_denoiser<20>(D, R, grid, flagged); break;
+    case 24: run_denoiser<24>(D, R, grid, flagged); break;
+    case 32: run_denoiser<32>(D, R, grid, flagged); break;
     default: return -3;
   }
   return 0;

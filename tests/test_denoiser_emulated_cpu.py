@@ -1,5 +1,6 @@
 """CPU execution of the fp32 DENOISER KERNEL SOURCE (csrc/denoiser.cuh: the persistent cooperative kernel that runs the 43
-barrier-separated stages of a diffusion step and the fused DDPM update) through the execution-model emulation of
+stages of a diffusion step and the fused DDPM update; both stage hand-overs: flag-carrying activation words -- the buffers
+start out full of stale-version NaN words, so accepting a wrong version fails the comparison -- and group barriers) through the execution-model emulation of
 tests/host/cuda_emu.h, against the fixtures produced by the reference's own `Denoiser` / `GaussianDiffusion` modules.
 Weights are re-laid out exactly as pdb_denoiser_load does it (restated as host loops in tests/host/kernels_emu.cpp).
 Same tolerances as the GPU parity tests.  Test infrastructure: kernel logic only, see tests/test_ggs_emulated_cpu.py."""
@@ -22,6 +23,12 @@ def emu():
     lib = C.CDLL(entry.build_emulator())
     lib.denoiser_emu_run.restype = C.c_int
     return lib
+
+
+@pytest.fixture(autouse=True, params=["flags", "barriers"])
+def handover(request, monkeypatch):
+    monkeypatch.setenv("PDB_DEN_FLAG", "1" if request.param == "flags" else "0")  # read by tests/host/kernels_emu.cpp per run
+    return request.param
 
 
 @pytest.fixture(scope="module")
@@ -86,3 +93,16 @@ def test_emulated_multi_step_launch_equals_single_steps(emu, weights):
         np.testing.assert_array_equal(one["x"], fused["trail"][1 + k])
         cur = one["x"]
     np.testing.assert_array_equal(fused["x"], cur)
+
+
+def test_emulated_sequence_spanning_token_tiles(emu, weights):
+    """A sequence cut into several token tiles (20 frames, tiles of 8): attention items read key / value rows that other tiles'
+    items own (the case the flag-carrying qkv buffer is double buffered for); two steps in one launch, odd grid sizes."""
+    g = load_golden("p_sample.npz")
+    rng = np.random.default_rng(1)
+    draws = rng.normal(size=(101, 20, 9)).astype(np.float32)
+    want = run_steps(emu, weights, g["t99_x"], g["z"], 99, 98, draws=draws, grid=4, token_tile=20)
+    for grid in (5, 7):
+        got = run_steps(emu, weights, g["t99_x"], g["z"], 99, 98, draws=draws, grid=grid, token_tile=8)
+        np.testing.assert_allclose(got["x"], want["x"], rtol=0, atol=2e-5 * np.abs(want["x"]).max())
+        np.testing.assert_allclose(got["eps"], want["eps"], rtol=0, atol=3e-5)

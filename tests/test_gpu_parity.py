@@ -430,6 +430,67 @@ def test_host_buffer_entry_equals_device_entry(sampler, dev):
     assert not np.allclose(pose_h[0], pose_h[1])
 
 
+@pytest.mark.parametrize("B,N", [(1, 20), (2, 20), (1, 5), (3, 13), (1, 80)])
+def test_denoiser_handover_modes_bit_identical(sampler, dev, B, N):
+    """The two stage hand-overs of the persistent denoiser kernel (group barriers = default, flag-carrying activation words)
+    run the same arithmetic in the same order: the whole unguided trajectory (100 steps, one launch) is bit-identical.
+    Run twice in the flagged mode: the second launch reuses buffers that hold the first launch's (older-version) words."""
+    ctx = sampler.model.native_context()
+    z = syn.random_features(B, N, 5).to(dev)
+    draws = syn.predraw_noise(B, N, seed=5).to(dev)
+    try:
+        ctx.set_denoiser_engine("fp32")
+        ctx.set_denoiser_handover(False)
+        pose_a, trail_a, _ = ctx.sample_loop(z, draws, None, None, 0)
+        ctx.set_denoiser_handover(True)
+        pose_b, trail_b, _ = ctx.sample_loop(z, draws, None, None, 0)
+        pose_c, trail_c, _ = ctx.sample_loop(z, draws, None, None, 0)
+    finally:
+        ctx.set_denoiser_handover(False)
+        ctx.set_denoiser_engine("auto")
+    assert torch.isfinite(trail_a).all()
+    assert torch.equal(trail_a, trail_b) and torch.equal(pose_a, pose_b)
+    assert torch.equal(trail_a, trail_c) and torch.equal(pose_a, pose_c)
+
+
+def test_host_matches_entry_equals_pack_then_host_entry(sampler, dev):
+    """pdb_sample_loop_host_matches (reference-format matches in, packing overlapped with the unguided steps) ==
+    pdb_matches_pack + pdb_sample_loop_host; bad input is rejected and leaves the context usable."""
+    ctx = sampler.model.native_context()
+    frames = 6
+    sets = [syn.scene_matches(frames, 48 + 16 * s, seed=71 + s)[0] for s in range(2)]
+    cfg = syn.default_ggs_cfg()
+    cfg.update(iter_num=3, min_matches=0, verbose=False)
+    z = syn.random_features(2, frames, 71).numpy()
+    draws = syn.predraw_noise(2, frames, seed=71).numpy()
+    for start in (10, 0, 100):  # usual split; guidance never starts; no unguided prefix at all
+        packs = [ctx.pack_matches(m) for m in sets]
+        want, want_trail = np.zeros((2, frames, 9), np.float32), np.zeros((101, 2, frames, 9), np.float32)
+        want_stats = np.zeros(max(start, 1) * 2, dtype=_native.GGS_STATS_DTYPE)
+        ctx.sample_loop_host(z, draws, packs, cfg, start, want, want_trail, want_stats)
+        got, got_trail = np.zeros_like(want), np.zeros_like(want_trail)
+        got_stats = np.zeros_like(want_stats)
+        ctx.sample_loop_host_matches(z, draws, sets, cfg, start, got, got_trail, got_stats)
+        np.testing.assert_array_equal(got_trail[: 101 - start], want_trail[: 101 - start])  # unguided part: no atomics
+        if start == 100:
+            # guidance on pure noise with random weights diverges (both runs; the summation order of the exchange differs between
+            # two launches and the divergence amplifies it): only the bookkeeping is comparable
+            assert (got_stats["iters"] > 0).all() and (want_stats["iters"] > 0).all()  # all 100 x 2 guided steps ran
+            continue
+        scale = np.abs(want_trail).max()
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-3 * scale)
+        assert np.array_equal(got_stats["iters"], want_stats["iters"])
+    bad = dict(sets[0])
+    bad["i12"] = np.array(bad["i12"]).copy()
+    bad["i12"][3, 1] = frames
+    with pytest.raises(ValueError, match="outside"):
+        ctx.sample_loop_host_matches(z, draws, [sets[0], bad], cfg, 10, got)
+    with pytest.raises(ValueError, match="one per sequence"):
+        ctx.sample_loop_host_matches(z, draws, sets[:1], cfg, 10, got)
+    ctx.sample_loop_host_matches(z, draws, sets, cfg, 10, got)  # still usable
+    assert np.isfinite(got).all()
+
+
 def test_pose_diffusion_model_api(dev, golden_state):
     model = pdb.PoseDiffusionModel(
         pose_encoding_type="absT_quaR_logFL", IMAGE_FEATURE_EXTRACTOR=None,
