@@ -484,6 +484,7 @@ def main():
         "config": {"workload": desc, "frames": frames, "matches_per_pair": per_pair, "sequences_per_gpu": B, "denoiser_engine": args.denoiser_engine, "ggs_layout": args.ggs_layout, "timesteps": T_STEPS,
                    "parallelism": f"sequences sharded over {world} GPU(s), final all-gather of poses only",
                    "l2": "flushed between timed loops (256 MiB write); within a launch the match set is deliberately kept on chip when it fits",
+                   "outputs": "final pose only; the optional pose_process trajectory (models/gaussian_diffuser.py:298-300, 72 KB per sequence) is not materialised in the timed loops",
                    "weights": "random init (reference init law), z ~ N(0,1), uniform-random correspondences"},
         "e2e": {"value": e2e_value, "unit": "diffusion steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "C-ABI pdb_sample_loop_host_matches with pinned host buffers: reference-format float64/int64 matches are "

@@ -294,11 +294,15 @@ class Context:
         self._ok(self.lib.pdb_ggs_layout(self.handle, GGS_LAYOUTS[layout]), "pdb_ggs_layout")
         self.ggs_layout = layout
 
-    def tc_linear(self, x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, relu: bool = False) -> torch.Tensor:
-        """Y = relu?(x @ w^T + bias + residual) on the tcgen05 tensor cores (TF32 products, fp32 accumulate)."""
+    def tc_linear(self, x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, relu: bool = False,
+                  in_place: bool = False) -> torch.Tensor:
+        """Y = relu?(x @ w^T + bias + residual) on the tcgen05 tensor cores (TF32 products, fp32 accumulate).
+        in_place: Y is the residual buffer itself (the denoiser's residual-stream update; small problems then split K)."""
         S, K = x.shape
         O = w.shape[0]
-        y = torch.empty(S, O, device=self.device)
+        if in_place and residual is None:
+            raise ValueError("in_place needs a residual")
+        y = residual if in_place else torch.empty(S, O, device=self.device)
         self._ok(self.lib.pdb_debug_tc_linear(self.handle, x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
                                               residual.data_ptr() if residual is not None else None, y.data_ptr(), S, O, K,
                                               int(relu), _stream_ptr(self.device)), "pdb_debug_tc_linear")

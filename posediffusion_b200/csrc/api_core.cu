@@ -101,6 +101,7 @@ int pdb_create(pdb_context** out, int device_ordinal) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (const char* lay = getenv("PDB_GGS_LAYOUT")) ctx->ggs_layout = (lay[0] == 'p' && lay[1] == 'a') ? kLayoutPaired : kLayoutPlain;
   if (const char* f = getenv("PDB_DEN_FLAG")) ctx->den_flag = atoi(f) != 0;
+  if (const char* f = getenv("PDB_TC_PDL")) ctx->tc_pdl = atoi(f) != 0;
   *out = reinterpret_cast<pdb_context*>(ctx);
   return PDB_OK;
 }

@@ -25,6 +25,23 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+// Kernel launch, optionally as a programmatic dependent of the previous launch in the stream (csrc/common.cuh: pdl_wait /
+// pdl_trigger).  Inside a stream capture this becomes a programmatic edge of the graph.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // 2-D fp32 row-major [rows, K] tensor, box = box_rows x 32 floats (128 bytes), 128-byte swizzle, zero fill out of bounds
 int make_map(Context* ctx, CUtensorMap* map, const float* ptr, int rows, int K, int box_rows) {
   auto encode = get_encode();
@@ -55,11 +72,12 @@ static int launch_tc_linear(Context* ctx, const float* X, const float* W, const 
     PDB_CUDA(ctx, cudaFuncSetAttribute(tc_linear_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const int tiles = (E.O / BN) * ((E.S + kTcBM - 1) / kTcBM);
-  const int grid = std::min(tiles, 2 * ctx->sm_count);  // two CTAs per SM (shared memory and 2 x 2BN <= 512 TMEM columns allow it)
+  const int tiles = (E.O / BN) * ((E.S + kTcBM - 1) / kTcBM) * (E.splits > 1 ? E.splits : 1);
+  // two CTAs per SM where the ring allows it (shared memory and 2 x 2BN <= 512 TMEM columns); the 8-deep ring fills an SM
+  const int grid = std::min(tiles, (2 * smem <= ctx->smem_optin ? 2 : 1) * ctx->sm_count);
   {
     ScopedTimer timer(ctx, st, 1);
-    tc_linear_kernel<BN, ST><<<grid, kTcThreads, smem, st>>>(mx, mw, E);
+    PDB_CUDA(ctx, launch_chained(tc_linear_kernel<BN, ST>, dim3(grid), dim3(kTcThreads), smem, st, E.pdl != 0, mx, mw, E));
   }
   PDB_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
@@ -88,29 +106,61 @@ static int launch_tc_linear_swap(Context* ctx, const float* X, const float* W, c
   return PDB_OK;
 }
 
+// Swap-AB tiles are taken for at most 96 tokens when enabled (pdb_debug_tc_swap / PDB_TC_SWAP=1).  Default off: without split-K
+// only O/128 CTAs stream the weights and the tile is bound by one SM's L2 bandwidth (profiles/r2_bench_tc_small.json: slower
+// than padding the tokens to a 128-row tile except at 5 tokens).
+static bool tc_linear_swapped(const Context* ctx, int S, int O) {
+  static const bool env_on = [] { const char* v = getenv("PDB_TC_SWAP"); return v && v[0] == '1'; }();
+  return S <= 96 && O % kTcBM == 0 && (env_on || ctx->tc_swap);
+}
+
 // Y = epilogue(X[S,K] @ W[O,K]^T) on the tensor cores.  K % 32 == 0, O % 64 == 0, all pointers 16-byte aligned.
 // 128-feature tiles (UMMA 128x128x8) when they still fill the machine, 64-feature tiles for the small-S denoiser shapes,
 // swap-AB tiles (weights on the M side) for at most 96 tokens when enabled (pdb_debug_tc_swap / PDB_TC_SWAP=1).
 int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st) {
   if (E.K % kTcBK || E.O % 64 || E.S < 1) return ctx->fail(PDB_ERR_INVALID, "tc_linear shape (S=%d, O=%d, K=%d)", E.S, E.O, E.K);
-  if (E.S <= 96 && E.O % kTcBM == 0) {
-    // default off: without split-K only O/128 CTAs stream the weights and the tile is bound by one SM's L2 bandwidth
-    // (profiles/r2_bench_tc_small.json: slower than padding the tokens to a 128-row tile except at 5 tokens)
-    static const bool env_on = [] { const char* v = getenv("PDB_TC_SWAP"); return v && v[0] == '1'; }();
-    if (env_on || ctx->tc_swap) {
-      if (E.S <= 32) return launch_tc_linear_swap<32>(ctx, X, W, E, ctx->attr_tc_swap[0], st);
-      if (E.S <= 64) return launch_tc_linear_swap<64>(ctx, X, W, E, ctx->attr_tc_swap[1], st);
-      return launch_tc_linear_swap<96>(ctx, X, W, E, ctx->attr_tc_swap[2], st);
-    }
+  if (tc_linear_swapped(ctx, E.S, E.O)) {
+    E.splits = 1;
+    E.stats = 0;
+    if (E.S <= 32) return launch_tc_linear_swap<32>(ctx, X, W, E, ctx->attr_tc_swap[0], st);
+    if (E.S <= 64) return launch_tc_linear_swap<64>(ctx, X, W, E, ctx->attr_tc_swap[1], st);
+    return launch_tc_linear_swap<96>(ctx, X, W, E, ctx->attr_tc_swap[2], st);
   }
   E.vec8 = (reinterpret_cast<uintptr_t>(E.Y) % 32 == 0) && (E.ldy % 8 == 0) &&
            (!E.residual || (reinterpret_cast<uintptr_t>(E.residual) % 32 == 0 && E.ldr % 8 == 0));
   const long long wide_tiles = (long long)(E.O / 128) * ((E.S + kTcBM - 1) / kTcBM);
   if (E.O % 128 == 0 && wide_tiles >= ctx->sm_count) {  // (measured: relaxing this to 85 % of the SMs is slower, 1.79 vs 1.67 ms per 20 frames)
     // 3 x 32 KB ring: two CTAs per SM, the epilogue of one under the main loop of the other (measured 1.16-1.26x over 4 x 32 KB)
+    E.splits = 1;
+    E.stats = 0;
     return launch_tc_linear<128, 3>(ctx, X, W, E, ctx->attr_tc128, st);
   }
+  if (E.allow_small && tc_linear_small(ctx, E.S, E.O)) {
+    // Fewer 64-feature tiles than SMs (the denoiser at a few hundred tokens): a CTA's k-loop is a serial chain of TMA round
+    // trips, so (i) an 8-deep ring keeps 192 KB in flight per SM instead of 96, (ii) GEMMs that update the residual stream in
+    // place are split along K over the idle SMs, the partial products added to Y with vector reductions, and (iii) the folded
+    // LayerNorm statistics come out of the X tiles inside the kernel (E.stats, requested by the caller).
+    const int tiles = (E.O / 64) * ((E.S + kTcBM - 1) / kTcBM), num_kb = E.K / kTcBK;
+    E.splits = 1;
+    const bool in_place = E.residual == E.Y && E.ldr == E.ldy && !E.relu && !E.gelu && !E.colsum && E.vec8;
+    if (in_place)
+      for (int s : {8, 4, 2})
+        if (num_kb % s == 0 && num_kb / s >= 2 && tiles * s <= ctx->sm_count) {
+          E.splits = s;
+          break;
+        }
+    if (!E.colsum || E.splits != 1) E.stats = 0;
+    return launch_tc_linear<64, 8>(ctx, X, W, E, ctx->attr_tc_deep, st);
+  }
+  E.splits = 1;
+  E.stats = 0;
   return launch_tc_linear<64, kTcStages>(ctx, X, W, E, ctx->attr_tc, st);
+}
+
+// the launcher's "small problem" regime (see above); callers that want in-kernel LayerNorm statistics ask first
+bool tc_linear_small(const Context* ctx, int S, int O) {
+  if (tc_linear_swapped(ctx, S, O)) return false;
+  return (long long)(O / 64) * ((S + kTcBM - 1) / kTcBM) <= ctx->sm_count && !getenv("PDB_TC_NO_SMALL");
 }
 
 }  // namespace pdb
@@ -132,6 +182,7 @@ extern "C" int pdb_debug_tc_linear(pdb_context* c, const float* x_dev, const flo
   E.O = O;
   E.K = K;
   E.relu = relu;
+  E.allow_small = 1;
   return enqueue_tc_linear(ctx, x_dev, w_dev, E, static_cast<cudaStream_t>(stream));
 }
 
@@ -145,6 +196,8 @@ extern "C" int pdb_debug_tc_linear(pdb_context* c, const float* x_dev, const flo
 namespace {
 
 __global__ void embed_kernel(const float* __restrict__ x, float* __restrict__ emb, int S) {  // [S,9] -> [S,256] harmonic features
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * kPoseEmbPad) return;
   const int s = i / kPoseEmbPad, col = i - s * kPoseEmbPad;
@@ -164,6 +217,8 @@ __global__ void pivot_add_kernel(float* __restrict__ zproj, const float* __restr
   if (i < batch * kDM) zproj[(size_t)(i / kDM) * frames * kDM + (i % kDM)] += w_pivot[i % kDM];
 }
 __global__ void row_stats_kernel(const float* __restrict__ h, float* __restrict__ mean, float* __restrict__ rstd, int S) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= S) return;
   const float4* p = reinterpret_cast<const float4*>(h + (size_t)row * kDM);
@@ -189,18 +244,25 @@ __global__ void row_stats_kernel(const float* __restrict__ h, float* __restrict_
 }
 __global__ void __launch_bounds__(kDenThreads) attention_kernel(const float* __restrict__ qkv, float* __restrict__ att, int frames) {
   extern __shared__ __align__(16) float att_smem[];
+  pdl_trigger();
+  pdl_wait();
   const int chunks = (frames + kDenWarps - 1) / kDenWarps;
   const int item = blockIdx.x;
   attention_item<false>(att_smem, qkv, att, item / (kHeads * chunks), (item / chunks) % kHeads, item % chunks, frames, 0u, 0u);
 }
 // the timestep lives on the device (tstate = {t, t_lo}) so that one captured graph serves every diffusion step
 __global__ void __launch_bounds__(kDenThreads) tail_kernel(const __grid_constant__ DenoiserDev W, const __grid_constant__ DenoiserRun R, const int* __restrict__ tstate) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x * kDenWarps + (threadIdx.x >> 5);
   const int t = tstate[0];
   if (s < R.tokens) tail_token<false>(W, R, s, t, t == tstate[1], 0u, 0u);
 }
 __global__ void step_set_kernel(int* tstate, int t, int t_lo) { tstate[0] = t; tstate[1] = t_lo; }
-__global__ void step_dec_kernel(int* tstate) { tstate[0] -= 1; }
+__global__ void step_dec_kernel(int* tstate) {
+  pdl_wait();
+  tstate[0] -= 1;
+}
 
 }  // namespace
 
@@ -223,12 +285,16 @@ int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
   float* emb = ws; ws += (size_t)S * kPoseEmbPad;
   float* mean = ws; ws += S;
   float* rstd = ws;
+  bool pdl = false;  // set while a step is being enqueued
   auto lin = [&](const float* X, const float* Wm, int O, int K, const float* bias, const int* t_ptr, const float* residual, int ldr,
                  const float* colsum, float* Y, int relu, cudaStream_t s) {
     TcEpilogue E = {};
     E.bias = bias; E.t_ptr = t_ptr; E.bias_t_stride = kDM; E.residual = residual; E.ldr = ldr;
     E.colsum = colsum; E.row_mean = colsum ? mean : nullptr; E.row_rstd = colsum ? rstd : nullptr;
     E.Y = Y; E.ldy = O; E.S = S; E.O = O; E.K = K; E.relu = relu;
+    E.allow_small = 1;
+    E.pdl = pdl;
+    E.stats = colsum && tc_linear_small(ctx, S, O);  // then no row_stats_kernel precedes this GEMM (below)
     return enqueue_tc_linear(ctx, X, Wm, E, s);
   };
   const size_t att_smem = sizeof(float) * ((size_t)N * (kHD + 4) + (size_t)N * kHD + 2 * kDenWarps * kHD) + 64;
@@ -246,29 +312,36 @@ int enqueue_denoiser_tc(Context* ctx, DenoiserRun run, cudaStream_t st) {
     pivot_add_kernel<<<(B * kDM + 255) / 256, 256, 0, st>>>(run.zproj, T.w_pivot, B, N);
     ctx->launches += 1;
   }
-  // ---- one diffusion step = 60 launches; captured once per buffer set, replayed per step ----
+  // ---- one diffusion step = 60 launches (44 when the LayerNorm statistics are computed inside the QKV / FF1 GEMMs);
+  // captured once per buffer set, replayed per step ----
+  const bool stats_qkv = tc_linear_small(ctx, S, 3 * kDM), stats_ff1 = tc_linear_small(ctx, S, kFF);
   auto enqueue_step = [&](cudaStream_t s) -> int {
-    embed_kernel<<<(S * kPoseEmbPad + 255) / 256, 256, 0, s>>>(run.x, emb, S);
+    // the kernels of a step form one programmatic chain (the first one has no predecessor in the capture).  Measured on the
+    // denoiser per 100 steps: 160 tokens 34.7 -> 33.1 ms, 640 tokens 41.5 -> 43.3 ms, 2560 tokens 69.8 -> 70.1 ms: small steps only
+    pdl = ctx->tc_pdl && S <= 320;
+    PDB_CUDA(ctx, launch_chained(embed_kernel, dim3((S * kPoseEmbPad + 255) / 256), dim3(256), 0, s, false, (const float*)run.x, emb, S));
     if (int rc = lin(emb, T.wx, kDM, kPoseEmbPad, T.tproj, tstate, run.zproj, kDM, nullptr, run.h, 0, s)) return rc;
     for (int l = 0; l < kLayers; ++l) {
       const TcLayer& L = T.layer[l];
-      row_stats_kernel<<<(S + 7) / 8, 256, 0, s>>>(run.h, mean, rstd, S);
+      if (!stats_qkv) PDB_CUDA(ctx, launch_chained(row_stats_kernel, dim3((S + 7) / 8), dim3(256), 0, s, pdl, (const float*)run.h, mean, rstd, S));
       if (int rc = lin(run.h, L.wqkv, 3 * kDM, kDM, L.bias_qkv, nullptr, nullptr, 0, L.colsum_qkv, run.qkv, 0, s)) return rc;
-      attention_kernel<<<B * kHeads * chunks, kDenThreads, att_smem, s>>>(run.qkv, run.att, N);
+      PDB_CUDA(ctx, launch_chained(attention_kernel, dim3(B * kHeads * chunks), dim3(kDenThreads), att_smem, s, pdl, (const float*)run.qkv, run.att, N));
       if (int rc = lin(run.att, L.wout, kDM, kDM, L.bout, nullptr, run.h, kDM, nullptr, run.h, 0, s)) return rc;
-      row_stats_kernel<<<(S + 7) / 8, 256, 0, s>>>(run.h, mean, rstd, S);
+      if (!stats_ff1) PDB_CUDA(ctx, launch_chained(row_stats_kernel, dim3((S + 7) / 8), dim3(256), 0, s, pdl, (const float*)run.h, mean, rstd, S));
       if (int rc = lin(run.h, L.wff1, kFF, kDM, L.bias_ff1, nullptr, nullptr, 0, L.colsum_ff1, run.ff, 1, s)) return rc;
       if (int rc = lin(run.ff, L.wff2, kDM, kFF, L.bff2, nullptr, run.h, kDM, nullptr, run.h, 0, s)) return rc;
     }
     if (int rc = lin(run.h, T.wlast0, kHid, kDM, T.blast0, nullptr, nullptr, 0, nullptr, run.u, 0, s)) return rc;
-    tail_kernel<<<(S + kDenWarps - 1) / kDenWarps, kDenThreads, 0, s>>>(w->dev, run, tstate);
-    step_dec_kernel<<<1, 1, 0, s>>>(tstate);
+    PDB_CUDA(ctx, launch_chained(tail_kernel, dim3((S + kDenWarps - 1) / kDenWarps), dim3(kDenThreads), 0, s, pdl, w->dev, run, (const int*)tstate));
+    PDB_CUDA(ctx, launch_chained(step_dec_kernel, dim3(1), dim3(1), 0, s, pdl, tstate));
+    pdl = false;
     return PDB_OK;
   };
-  constexpr int kNodes = 2 + kLayers * 7 + 3;
+  const int kNodes = 2 + kLayers * (7 - (stats_qkv ? 1 : 0) - (stats_ff1 ? 1 : 0)) + 3;
   std::vector<size_t> key = {(size_t)S, (size_t)B, (size_t)N, (size_t)run.guide_below, (size_t)ctx->den_ws, (size_t)run.x,
                              (size_t)run.draws, (size_t)run.trail, (size_t)run.eps_out, (size_t)run.x0_out, (size_t)run.mean_out,
-                             (size_t)w->tc_arena};
+                             (size_t)w->tc_arena, (size_t)ctx->tc_swap, (size_t)stats_qkv, (size_t)stats_ff1,
+                             (size_t)tc_linear_small(ctx, S, kDM), (size_t)(ctx->tc_pdl && S <= 320)};  // launcher regime: the captured kernels differ
   if (!ctx->tc_graph || ctx->tc_graph_key != key) {
     if (ctx->tc_graph) { cudaGraphExecDestroy(ctx->tc_graph); ctx->tc_graph = nullptr; }
     if (!ctx->tc_capture_stream) PDB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->tc_capture_stream, cudaStreamNonBlocking));

@@ -82,6 +82,8 @@ inline void st_ll(unsigned long long* p, unsigned bits, unsigned tag) {
   __atomic_store_n(p, ((unsigned long long)tag << 32) | (unsigned long long)bits, __ATOMIC_RELAXED);
 }
 inline unsigned long long ld_ll(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void pdl_wait() {}
+inline void pdl_trigger() {}
 inline void ld_ll2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   a = __atomic_load_n(p, __ATOMIC_RELAXED);
   b = __atomic_load_n(p + 1, __ATOMIC_RELAXED);
@@ -157,6 +159,12 @@ __device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p)
   asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return w;
 }
+// Programmatic dependent launch (kernels chained inside the tensor-core engine's step graph): `pdl_trigger` lets the next kernel
+// of the chain start its prologue (barrier init, TMEM allocation, descriptor prefetch) while this one is still running;
+// `pdl_wait` blocks until the previous kernel has completed and its writes are visible.  Both are no-ops in a kernel that was
+// not launched with the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // two neighbouring words with one 16-byte access (16-byte aligned); each 64-bit element is single-copy atomic on its own
 __device__ __forceinline__ void ld_ll2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.relaxed.gpu.global.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");

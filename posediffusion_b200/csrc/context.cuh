@@ -47,7 +47,8 @@ struct Context {
   int tc_graph_nodes = 0;
   // cudaFuncSetAttribute is per device: remember per context (= per device) what was already requested
   size_t attr_ggs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, attr_den[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, attr_att = 0;
-  bool attr_tc = false, attr_tc128 = false;
+  bool attr_tc = false, attr_tc128 = false, attr_tc_deep = false;
+  bool tc_pdl = true;  // programmatic dependent launch between the kernels of the tensor-core engine's step graph (PDB_TC_PDL=0: off)
   bool tc_swap = false;     // swap-AB tcgen05 tiles for <= 96 tokens (pdb_debug_tc_swap); default off, see profiles/r2_bench_tc_small.json
   bool attr_tc_swap[3] = {false, false, false};  // swap-AB instantiations (32 / 64 / 96 tokens on the N side)
   // image feature extractor (csrc/api_vit.cu)

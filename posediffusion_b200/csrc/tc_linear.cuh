@@ -41,6 +41,13 @@ struct TcEpilogue {
   int relu;
   int gelu;  // exact (erf) GELU, torch.nn.functional.gelu default
   int vec8;  // set by the launcher: Y / residual rows are 32-byte aligned -> 256-bit global accesses
+  int pdl;          // launch with programmatic stream serialization (the kernel's prologue overlaps the previous kernel's tail)
+  int allow_small;  // caller opts in to the small-problem regime below (split-K sums in arrival order: not bit-reproducible)
+  // Small problems (fewer tiles than SMs), set by the launcher:
+  int splits;  // split-K factor (>= 1).  > 1: Y already holds the residual (in-place residual stream); every split adds its
+               // partial product to it with vector reductions (red.global.add.v4.f32), split 0 also the bias.
+  int stats;   // 1: the folded-LayerNorm row statistics are computed inside the kernel, by the epilogue warps, from the X
+               // operand tiles as they pass through shared memory (row_mean / row_rstd are not read); needs splits == 1
 };
 
 __host__ __device__ inline size_t tc_smem_bytes(int BN, int stages = kTcStages) {
@@ -105,9 +112,18 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&r)[8]) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
-// Persistent: every CTA walks the tile list (tile = blockIdx.x, + gridDim.x, ...; feature-tile index fastest so that CTAs running
-// side by side share the same 128 token rows in L2).  The accumulator is double buffered in TMEM (2 x BN columns): while the four
+// Persistent: every CTA walks the work list (work = blockIdx.x, + gridDim.x, ...; work = split * tiles + tile, feature-tile index
+// fastest so that CTAs running side by side share the same 128 token rows in L2; split s of E.splits covers the k-blocks
+// [s, s+1) * K/32 / splits).  The accumulator is double buffered in TMEM (2 x BN columns): while the four
 // epilogue warps drain tile i, the TMA and MMA warps are already inside tile i+1.
 template <int BN, int ST = kTcStages, bool kSwap = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -127,19 +143,23 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(tc_smem_raw + (tmem_slot - raw));
 
+  pdl_trigger();  // the next kernel of a programmatic chain may start its own prologue now (it still waits for our completion)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = E.K / kTcBK;
   // tile list: the N-side index runs fastest.  normal: M side = 128 tokens, N side = BN features; swap: M side = 128 features,
   // N side = BN tokens.  (m0, n0) below are always (M-side offset, N-side offset).
   const int n_tiles = kSwap ? (E.S + BN - 1) / BN : E.O / BN;
   const int total_tiles = n_tiles * (kSwap ? E.O / kTcBM : (E.S + kTcBM - 1) / kTcBM);
+  const int splits = kSwap ? 1 : (E.splits > 1 ? E.splits : 1);
+  const int total_work = total_tiles * splits;
+  const bool stats = !kSwap && E.stats && splits == 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < ST; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), stats ? 1 + 4 : 1);  // MMA commit (+ one arrival per epilogue warp that read the X tile for the row statistics)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
@@ -155,13 +175,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  pdl_wait();  // everything above touched only this CTA's shared memory / TMEM; global reads and writes start below
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work % total_tiles, split = work / total_tiles;
         const int m0 = (tile / n_tiles) * kTcBM, n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int kb0 = split * num_kb / splits, kb1 = (split + 1) * num_kb / splits;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % ST;
           const uint32_t ph = (it / ST) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
@@ -175,12 +198,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     if (lane == 0) {  // ===== MMA issuer =====
       const uint32_t idesc = umma_idesc_tf32(kTcBM, BN);
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++lt) {
+        const int split = work / total_tiles;
+        const int kb0 = split * num_kb / splits, kb1 = (split + 1) * num_kb / splits;
         const int buf = lt & 1;
         mbar_wait(tmem_empty_bar(buf), ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this buffer (passes at first use)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_acc + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % ST;
           const uint32_t ph = (it / ST) & 1;
           mbar_wait(full_bar(s), ph);
@@ -189,7 +214,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const uint64_t db = umma_desc_k128(base + s * kStageBytes + kABytes);
 #pragma unroll
           for (int k = 0; k < kTcBK / 8; ++k)  // advance 8 floats = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
-            umma_tf32(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_tf32(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((kb - kb0) | k) ? 1u : 0u);
           umma_commit(empty_bar(s));  // frees the slot once the MMAs that read it have retired
         }
         umma_commit(tmem_full_bar(buf));  // accumulator complete
@@ -199,10 +224,37 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int quarter = warp & 3;
     const float* bias = E.bias;
     if (bias && E.t_ptr) bias += (size_t)(*E.t_ptr) * E.bias_t_stride;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    int lt = 0, it = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++lt) {
+      const int tile = work % total_tiles, split = work / total_tiles;
       const int m0 = (tile / n_tiles) * kTcBM, n0 = (tile % n_tiles) * BN;
       const int buf = lt & 1;
+      // folded-LayerNorm statistics of this thread's token row, from the X tiles in the ring: a row is 128 contiguous bytes of a
+      // stage (SWIZZLE_128B only permutes the 16-byte chunks inside it, and a sum does not care); lane l starts at chunk l % 8 so
+      // that a warp's loads spread over all banks.  Shifted by the first value read (one-pass variance without cancellation).
+      float st_mean = 0.f, st_rstd = 1.f;
+      if (stats) {
+        float pivot = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % ST;
+          mbar_wait(full_bar(s), (it / ST) & 1);
+          const uint32_t rowaddr = base + s * kStageBytes + (uint32_t)(quarter * 32 + lane) * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = lds_f4(rowaddr + (uint32_t)(((j + lane) & 7) << 4));
+            if (kb == 0 && j == 0) pivot = x.x;
+            const float a = x.x - pivot, b = x.y - pivot, c = x.z - pivot, d = x.w - pivot;
+            s1 += (a + b) + (c + d);
+            s2 += (a * a + b * b) + (c * c + d * d);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(s));
+        }
+        const float inv_k = 1.0f / (float)E.K;
+        const float m = s1 * inv_k;
+        st_mean = pivot + m;
+        st_rstd = 1.0f / sqrtf(fmaxf(s2 * inv_k - m * m, 0.f) + 1e-5f);
+      }
       mbar_wait(tmem_full_bar(buf), (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if constexpr (kSwap) {
@@ -236,8 +288,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < E.S;
-      float mean = 0.f, rstd = 1.f;
-      if (E.colsum && row_ok) {
+      float mean = st_mean, rstd = st_rstd;
+      if (E.colsum && row_ok && !stats) {
         mean = E.row_mean[row];
         rstd = E.row_rstd[row];
       }
@@ -262,8 +314,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               const int col = n0 + c0 + j + t;
               float x = v[j + t];
               if (E.colsum) x = rstd * (x - mean * __ldg(E.colsum + col));
-              if (bias) x += __ldg(bias + col);
+              if (bias && split == 0) x += __ldg(bias + col);
               o[t] = x;
+            }
+            if (splits > 1) {  // Y holds the residual already: accumulate this split's partial product on top of it
+              red_add_v4(yrow + j, o[0], o[1], o[2], o[3]);
+              red_add_v4(yrow + j + 4, o[4], o[5], o[6], o[7]);
+              continue;
             }
             if (rrow) {
               float r[8];
@@ -306,5 +363,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 struct Context;
 // Y = epilogue(X[S,K] @ W[O,K]^T) on the tensor cores (csrc/api_tc.cu).  K % 32 == 0, O % 64 == 0, 16-byte aligned pointers.
 int enqueue_tc_linear(Context* ctx, const float* X, const float* W, TcEpilogue E, cudaStream_t st);
+// true when the launcher will treat (S, O) as a small problem: 8-deep ring, split-K for in-place residual GEMMs, and in-kernel
+// LayerNorm statistics when E.stats is set (the caller then skips its row-statistics kernel)
+bool tc_linear_small(const Context* ctx, int S, int O);
 
 }  // namespace pdb

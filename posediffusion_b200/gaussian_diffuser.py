@@ -21,20 +21,6 @@ from . import _native
 from .geometry_guided_sampling import format_log, geometry_guided_sampling, packed_matches
 
 
-def _linear_beta_schedule(timesteps):
-    scale = 1000 / timesteps
-    return torch.linspace(scale * 0.0001, scale * 0.02, timesteps, dtype=torch.float64)
-
-
-def _cosine_beta_schedule(timesteps, s=0.008):
-    import math
-
-    x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64)
-    ac = torch.cos(((x / timesteps) + s) / (1 + s) * math.pi * 0.5) ** 2
-    ac = ac / ac[0]
-    return torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
-
-
 class GaussianDiffusion(nn.Module):
     def __init__(self, timesteps=100, sampling_timesteps=None, beta_1=0.0001, beta_T=0.1, loss_type="l1",
                  objective="pred_noise", beta_schedule="custom", p2_loss_weight_gamma=0.0, p2_loss_weight_k=1):
@@ -44,12 +30,12 @@ class GaussianDiffusion(nn.Module):
         self.beta_1, self.beta_T = beta_1, beta_T
         self.loss_type, self.objective, self.beta_schedule = loss_type, objective, beta_schedule
         self.p2_loss_weight_gamma, self.p2_loss_weight_k = p2_loss_weight_gamma, p2_loss_weight_k
-        if beta_schedule == "linear":
-            betas = _linear_beta_schedule(timesteps)
-        elif beta_schedule == "cosine":
-            betas = _cosine_beta_schedule(timesteps)
-        elif beta_schedule == "custom":
+        if beta_schedule == "custom":  # the released configuration (cfgs/default.yaml); models/gaussian_diffuser.py:66-69
             betas = torch.linspace(beta_1, beta_T, timesteps, dtype=torch.float64)
+        elif beta_schedule in ("linear", "cosine"):
+            # the reference also offers these (:62-65); no released checkpoint uses them and the sm_100a sampler tabulates
+            # the custom schedule only -- refuse at construction instead of building buffers nothing can run
+            raise NotImplementedError(f"beta_schedule={beta_schedule!r}: only the released 'custom' schedule is built")
         else:
             raise ValueError(f"unknown beta schedule {beta_schedule}")
         self.num_timesteps = int(betas.shape[0])

@@ -64,6 +64,9 @@ def test_python_schedule_buffers_bit_exact():
         assert np.array_equal(state[k].numpy(), v), k
     with pytest.raises(ValueError):
         pdb.GaussianDiffusion(beta_schedule="nope")
+    for unbuilt in ("linear", "cosine"):  # offered by the reference, used by no released checkpoint: refused, not half-built
+        with pytest.raises(NotImplementedError):
+            pdb.GaussianDiffusion(beta_schedule=unbuilt)
 
 
 def test_state_dict_layout_matches_reference_checkpoint():
