@@ -16,8 +16,9 @@ timeout 300 python bench.py --steps 5 --warmup 3 --workload features --no-cpu-ba
 timeout 120 python tools/ggs_stage_probe.py 20 2048 > gpurun_out/ev_probe_ggs_cfg3.txt 2>&1
 timeout 300 python tools/ggs_stage_probe.py 80 4096 > gpurun_out/ev_probe_ggs_cfg5.txt 2>&1
 timeout 300 python tools/den_stage_probe.py 20 1 > gpurun_out/ev_probe_den_n20.txt 2>&1
+timeout 200 python tools/tc_gemm_probe.py 160 > gpurun_out/ev_tc_gemm_probe.txt 2>&1
 if [ -x build/stage_probe ]; then
-  (timeout 120 build/stage_probe 20 64 20000; timeout 120 build/stage_probe 20 128 20000; timeout 120 build/stage_probe 80 64 5000) > gpurun_out/ev_stage_probe.txt 2>&1
+  (timeout 120 build/stage_probe 20 64 20000; timeout 120 build/stage_probe 20 128 20000; timeout 120 build/stage_probe 8 64 20000) > gpurun_out/ev_stage_probe.txt 2>&1
 fi
 # launch list of one headline loop (duration-only pass)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/ev_launches_cfg3.csv \
