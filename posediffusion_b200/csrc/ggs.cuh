@@ -137,37 +137,10 @@ __device__ __forceinline__ void sampson_match2_unit(const float4 X, const float4
 // 16-loads-in-flight polling loops would otherwise compete for registers with the streaming loop of stage 1.
 template <bool kEval>
 __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned long long* xch2, float* accbase, int cpp, int cta, int group,
-                                          int N, unsigned it_global, const float* s_part, float* s_misc, int cta_cnt, float g_fx,
-                                          float g_fy, float* s_gsum, const int* s_expect, const int* s_mine, const float* s_pose,
-                                          bool upd_T, bool upd_R) {
+                                          int N, unsigned it_global, const float* s_part, const float* s_misc, int cta_cnt, float g_fx,
+                                          float g_fy, float* s_gsum, const int* s_expect, const int* s_mine) {
   const int tid = threadIdx.x;
   const int nsum = ggs_xch_words(N);
-  // The thread that receives the summed gradient entry e = (frame n, component c < 7) also starts the clip norms of stage 3:
-  // a2 = sum of the (selected) entries squared, p2 = squared pose entries where the gradient is non-zero (grad_mask, :117).
-  // Warp sums -> s_misc[16 + 2 warp], visible after the caller's block barrier; the 1 / n_valid^2 factor and the focal-length
-  // entries (global scalars times per-frame constants) are added by the caller.
-  float a2 = 0.f, p2 = 0.f;
-  auto note = [&](int e, float v) {
-    s_gsum[e] = v;
-    if (e < N * 7) {
-      const int n = e / 7, c = e - n * 7;
-      if (c < 3 ? upd_T : upd_R) {
-        a2 = fmaf(v, v, a2);
-        const float pm = (fabsf(v) > 0.f) ? s_pose[n * 9 + c] : 0.f;
-        p2 = fmaf(pm, pm, p2);
-      }
-    }
-  };
-  auto flush_norms = [&]() {
-    if ((tid & ~31) < nsum) {  // warps that received entries
-      a2 = warp_sum(a2);
-      p2 = warp_sum(p2);
-      if ((tid & 31) == 0) {
-        s_misc[16 + (tid >> 5) * 2] = a2;
-        s_misc[16 + (tid >> 5) * 2 + 1] = p2;
-      }
-    }
-  };
   if (accbase) {
     // ONE hop: a CTA adds {value, 1} to the accumulators of the frames its segments touch (s_mine; zeros if the gradient of a
     // touched frame happens to vanish) and to the five scalars; an accumulator of frame n expects s_expect[n] arrivals, a scalar
@@ -194,7 +167,7 @@ __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned lon
           if (v.y == want) break;
           ll_backoff();
         }
-        note(e, v.x);
+        s_gsum[e] = v.x;
       } else {
         unsigned long long w;
         for (;;) {
@@ -205,7 +178,6 @@ __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned lon
         s_gsum[e] = __uint_as_float((unsigned)w);
       }
     }
-    flush_norms();
     if (cta == 0) {
       float* old = accbase + (size_t)((it_global + 2u) % 3u) * nsum * kAccStride;
       for (int e = tid; e < nsum; e += kGgsThreads) st_pair_zero(old + (size_t)e * kAccStride);
@@ -238,13 +210,12 @@ __device__ __noinline__ void ggs_exchange(unsigned long long* xch1, unsigned lon
     }
     const unsigned long long* src = xch2 + buf * (size_t)groups * nsum;
     for (int e = tid; e < nsum; e += kGgsThreads)
-      note(e, __uint_as_float(e == nsum - 1 ? ll_sum<true>(src + e, nsum, groups, tag) : ll_sum<false>(src + e, nsum, groups, tag)));
+      s_gsum[e] = __uint_as_float(e == nsum - 1 ? ll_sum<true>(src + e, nsum, groups, tag) : ll_sum<false>(src + e, nsum, groups, tag));
   } else {
     const unsigned long long* src = xch1 + buf * (size_t)cpp * nsum;
     for (int e = tid; e < nsum; e += kGgsThreads)
-      note(e, __uint_as_float(e == nsum - 1 ? ll_sum<true>(src + e, nsum, cpp, tag) : ll_sum<false>(src + e, nsum, cpp, tag)));
+      s_gsum[e] = __uint_as_float(e == nsum - 1 ? ll_sum<true>(src + e, nsum, cpp, tag) : ll_sum<false>(src + e, nsum, cpp, tag));
   }
-  flush_norms();
 }
 
 // One CTA of the group that owns one sequence.  See the file header for the stage structure.
@@ -381,29 +352,6 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       }
       fpx = warp_sum(fx) * scale_over_N;
       fpy = warp_sum(fy) * scale_over_N;
-      if (warp == kGgsWarps - 1) {
-        // constants of the focal-length entries of the clip norms (stage 3), by a warp that owns no frame: sum of (fl * inr)^2 and
-        // of the squared log-focal pose entries where fl * inr != 0, x and y -> s_misc[48..51] (published by the barrier below)
-        float b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f;
-        for (int m = lane; m < N; m += 32) {
-          const float tx = s_fl[m * 2] * s_inr[m * 2], ty = s_fl[m * 2 + 1] * s_inr[m * 2 + 1];
-          b0 = fmaf(tx, tx, b0);
-          b1 = fmaf(ty, ty, b1);
-          const float px = (tx != 0.f) ? s_pose[m * 9 + 7] : 0.f, py = (ty != 0.f) ? s_pose[m * 9 + 8] : 0.f;
-          c0 = fmaf(px, px, c0);
-          c1 = fmaf(py, py, c1);
-        }
-        b0 = warp_sum(b0);
-        b1 = warp_sum(b1);
-        c0 = warp_sum(c0);
-        c1 = warp_sum(c1);
-        if (lane == 0) {
-          s_misc[48] = b0;
-          s_misc[49] = b1;
-          s_misc[50] = c0;
-          s_misc[51] = c1;
-        }
-      }
       kin[0] = 1.f / fpx;
       kin[1] = 1.f / fpy;
       kin[2] = -cx * kin[0];
@@ -779,8 +727,7 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
       if (kProbe && pr.dbg_clock && tid == 0) ck2 = clock64();
       // ================= exchange: all-reduce of the partial gradient over the CTAs of this sequence =================
       ggs_exchange<kEval>(pr.xch1, pr.xch2, P.xch_mode == 1 ? pr.acc : nullptr, cpp, cta, P.xch_group, N, it_global, s_part, s_misc, s_cta_cnt,
-                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum, s_expect, s_mine,
-                          s_pose, upd_T, upd_R);
+                          (-s_misc[8] + cx * s_misc[10]) / (fpx * fpx), (-s_misc[9] + cy * s_misc[11]) / (fpy * fpy), s_gsum, s_expect, s_mine);
       ++it_global;
       __syncthreads();
       if (kProbe && pr.dbg_clock && tid == 0) {
@@ -825,28 +772,47 @@ __device__ __forceinline__ void ggs_body(const GgsProblem& pr, const GgsParams& 
               }
             }
           } else {
-            // clip norms (:117-120).  The sums over the gT / gq entries were started by the threads that received them in the
-            // exchange (a2, p2 partials per warp in s_misc[16..], fixed order below: identical in every thread and CTA); the 1 / n
-            // factor is applied to the total, and the focal-length entries g = gf * fl_n * inr_n / n contribute gf^2 * s_misc[48..49]
-            // and, where non-zero, the squared pose entries s_misc[50..51] (per-frame constants summed in stage 0).
+            // clip norms: one element per thread (N9 <= 1152: up to three), warp sums, partials through shared memory
+            constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
+            float gv[kPer];
             float gn2 = 0.f, pn2 = 0.f;
-            const int warps_used = min(kGgsWarps, (nsum + 31) / 32);
-            for (int wv = 0; wv < warps_used; ++wv) {
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+              const int e = tid + q * kGgsThreads;
+              gv[q] = 0.f;
+              if (e < N9) {
+                const float g1 = grad_of(e);
+                gv[q] = g1;
+                gn2 = fmaf(g1, g1, gn2);
+                const float pm = (fabsf(g1) > 0.f) ? s_pose[e] : 0.f;  // grad_mask = grads.abs() > 0 (:117)
+                pn2 = fmaf(pm, pm, pn2);
+              }
+            }
+            const int warps_used = min(kGgsWarps, (N9 + 31) / 32);  // warps that hold elements (the others contribute zeros)
+            if (warp < warps_used) {
+              gn2 = warp_sum(gn2);
+              pn2 = warp_sum(pn2);
+              if (lane == 0) {
+                s_misc[16 + warp * 2] = gn2;
+                s_misc[16 + warp * 2 + 1] = pn2;
+              }
+            }
+            __syncthreads();
+            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: norm partials
+            gn2 = 0.f;
+            pn2 = 0.f;
+            for (int wv = 0; wv < warps_used; ++wv) {  // fixed order: identical in every thread and CTA
               gn2 += s_misc[16 + wv * 2];
               pn2 += s_misc[16 + wv * 2 + 1];
             }
-            gn2 = (inv_n * inv_n) * (gn2 + gfx * gfx * s_misc[48] + gfy * gfy * s_misc[49]);
-            pn2 += ((fabsf(gfx * inv_n) > 0.f) ? s_misc[50] : 0.f) + ((fabsf(gfy * inv_n) > 0.f) ? s_misc[51] : 0.f);
             const float max_norm = alpha_over_lr * sqrtf(pn2);       // alpha * |x . mask| / lr  (:119)
             const float cc = max_norm / (sqrtf(gn2) + 1e-6f);        // clip_grad_norm_
             const float coef = (cc > 1.0f) ? 1.0f : cc;              // clamp(max=1), NaN passes through
-            if (kProbe && pr.dbg_clock && tid == 0) { const long long c = clock64(); clk_sum[0] += c - ck3; ck3 = c; }  // probe: coefficient
-            constexpr int kPer = (kMaxFrames * 9 + kGgsThreads - 1) / kGgsThreads;
 #pragma unroll
             for (int q = 0; q < kPer; ++q) {
               const int e = tid + q * kGgsThreads;
               if (e < N9) {
-                const float g1 = grad_of(e) * coef;
+                const float g1 = gv[q] * coef;
                 const float v = (done == 0) ? g1 : fmaf(P.momentum, s_vel[e], g1);  // momentum buffer resets per phase
                 s_vel[e] = v;
                 const float pnew = s_pose[e] - P.lr * v;
