@@ -1,5 +1,5 @@
 #!/bin/bash
-set -u
+# A/B of the tensor-core engine launcher regimes: new (split-K + in-kernel statistics, with / without programmatic dependent launch) vs the previous launcher (PDB_TC_NO_SMALL=1).
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_features.py -m gpu -q > gpurun_out/tc_gputests.log 2>&1
